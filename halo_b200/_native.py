@@ -1,0 +1,123 @@
+"""ctypes binding of libhalo_sm100.so (the C ABI declared in include/halo_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing it is built with nvcc; if that
+fails, or a CUDA device is absent when a kernel is requested, the call raises.  Tensors cross the
+boundary as raw device pointers (`tensor.data_ptr()`), the stream as `torch.cuda.current_stream()`.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import _build
+
+_lock = threading.Lock()
+_lib = None
+
+# enums of include/halo_b200.h
+FEAT_TANGENT_F32, FEAT_BALL_F32, FEAT_BALL_F64 = 0, 1, 2
+PIXUNC_ENTROPY, PIXUNC_ONE_MINUS_PGT = 0, 1
+LABEL_ARGMAX, LABEL_GT_FILLED = 0, 1
+NORM_RADIUS, NORM_EUCLID = 0, 1
+UNC_BOXSUM, UNC_PIXEL, UNC_ZERO = 0, 1, 2
+PUR_NORM, PUR_LABEL_HIST, PUR_RADIUS_BINS, PUR_ZERO = 0, 1, 2, 3
+
+ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = -1, -2, -3, -4
+
+_vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+_SIGNATURES = {
+    "halo_abi_version": (_i, []),
+    "halo_last_error": (ctypes.c_char_p, []),
+    "halo_head_workspace_bytes": (_sz, [_i, _i]),
+    "halo_head_fwd": (_i, [_vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "halo_head_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "halo_head_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "halo_expmap0_project": (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _vp]),
+    "halo_ball_norm": (_i, [_vp, _i, _f, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "halo_logits_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "halo_score_workspace_bytes": (_sz, [_i]),
+    "halo_score": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "halo_select_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "halo_select_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "halo_select_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load (building first if needed) libhalo_sm100.so and type its entry points."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise RuntimeError("libhalo_sm100.so is missing: run `python -m halo_b200._build`")
+            _build.build()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the symbol is not exported: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        if lib.halo_abi_version() != 1:
+            raise RuntimeError("libhalo_sm100.so ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def last_error():
+    return load().halo_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    msg = "%s failed (%d): %s" % (what, rc, last_error())
+    if rc == ERR_BAD_ARG:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_of(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def require_cuda(t, name):
+    if not t.is_cuda:
+        raise RuntimeError(
+            "halo_b200: %s must be a CUDA tensor -- this package has no CPU path (got device %s)" % (name, t.device))
+    return t
+
+
+class Workspace:
+    """Grow-only uint8 device scratch, one per (device, purpose); owned by torch's allocator."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, device, key, nbytes):
+        k = (device.index, key)
+        buf = self._bufs.get(k)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+            self._bufs[k] = buf
+        return buf
+
+
+workspace = Workspace()

@@ -1,0 +1,142 @@
+"""Budgeted selection + acquisition driver -- B200 mirror of the reference's `core/active/build.py`.
+
+`select_pixels_to_label` (:27-64) keeps the reference's signature and its in-place semantics on all four
+tensors (the reference hands it a CUDA score, CPU bool `active`/`selected`, CUDA int64 `active_mask`/
+`ground_truth`); the sequential arg-max loop is replaced by the exact parallel form in `halo_select_*`.
+`RegionSelection` (:71-186) keeps its signature and side effects (eval()/train() toggles, uint8 mask PNG at
+`path_to_mask`, `{"active","selected"}` indicator at `path_to_indicator`).
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import _native as nat
+from .floating_region import FloatingRegionScore
+from .hyperbolic import PoincareEmbedding
+
+
+def select_planes(score, active, selected, active_mask, gt, n_regions, active_radius, mask_radius, want_picks=False):
+    """Batched in-place selection on device planes.  score (N,H,W) f32|f64; the rest (N,H,W) uint8.
+    Returns (n_picked (N,) int32 device tensor, picks (N,n_regions) int32 | None)."""
+    lib = nat.load()
+    nat.require_cuda(score, "score")
+    if score.dtype not in (torch.float32, torch.float64):
+        raise TypeError("select_planes: score must be float32 or float64")
+    for t, name in ((active, "active"), (selected, "selected"), (active_mask, "active_mask"), (gt, "ground_truth")):
+        if t.dtype != torch.uint8 or not t.is_contiguous() or t.device != score.device or t.shape != score.shape:
+            raise ValueError("select_planes: %s must be a contiguous uint8 tensor shaped like score on %s" % (name, score.device))
+    if not score.is_contiguous():
+        raise ValueError("select_planes: score must be contiguous")
+    N, H, W = score.shape
+    n_regions = int(n_regions)
+    dev = score.device
+    n_picked = torch.empty((N,), dtype=torch.int32, device=dev)
+    picks = torch.empty((N, max(n_regions, 1)), dtype=torch.int32, device=dev) if want_picks else None
+    ws = nat.workspace.get(dev, "select", lib.halo_select_workspace_bytes(N, H, W, n_regions))
+    fn = lib.halo_select_f64 if score.dtype == torch.float64 else lib.halo_select_f32
+    with torch.cuda.device(dev):
+        rc = fn(nat.ptr(score), nat.ptr(active), nat.ptr(selected), nat.ptr(active_mask), nat.ptr(gt), n_regions,
+                int(active_radius), int(mask_radius), nat.ptr(n_picked), nat.ptr(picks), N, H, W, nat.ptr(ws),
+                ws.numel(), nat.stream_of(score))
+    nat.check(rc, "halo_select")
+    return n_picked, picks
+
+
+def select_pixels_to_label(score, active_regions, active_radius, mask_radius, active, selected, active_mask,
+                           ground_truth):
+    """Reference `select_pixels_to_label` (build.py:27-64): mutates and returns (score, active, selected, active_mask).
+
+    Tensors may live anywhere (the reference keeps active/selected on the CPU): they are staged to uint8
+    device planes, selected on the GPU, and copied back IN PLACE."""
+    nat.require_cuda(score, "score")
+    dev = score.device
+    H, W = score.shape
+    s = score if (score.is_contiguous() and score.dtype in (torch.float32, torch.float64)) else score.float().contiguous()
+    act = active.to(device=dev, dtype=torch.uint8).contiguous().clone().view(1, H, W)
+    sel = selected.to(device=dev, dtype=torch.uint8).contiguous().clone().view(1, H, W)
+    msk = active_mask.to(device=dev, dtype=torch.uint8).contiguous().clone().view(1, H, W)
+    gt = ground_truth.to(device=dev, dtype=torch.uint8).contiguous().view(1, H, W)
+    select_planes(s.view(1, H, W), act, sel, msk, gt, active_regions, active_radius, mask_radius)
+    if s.data_ptr() != score.data_ptr():
+        score.copy_(s)
+    active.copy_(act[0].to(active.dtype))
+    selected.copy_(sel[0].to(selected.dtype))
+    active_mask.copy_(msk[0].to(active_mask.dtype))
+    return score, active, selected, active_mask
+
+
+def to_np_array(tensor):
+    return np.array(tensor.cpu().numpy(), dtype=np.uint8)
+
+
+def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_number):
+    """Reference `RegionSelection` (build.py:71-186): one acquisition round over the target pool on this rank.
+
+    Same loader item contract (core/datasets/cityscapes.py:274-286) and on-disk side effects.  The per-image
+    body runs the CUDA path: classifier head (fused when the classifier was built with this package's
+    HyperMapper/HyperMLR), FloatingRegionScore, select_pixels_to_label."""
+    from PIL import Image
+
+    feature_extractor.eval()
+    classifier.eval()
+
+    per_region_pixels = (2 * cfg.ACTIVE.RADIUS_K + 1) ** 2
+    active_radius = cfg.ACTIVE.RADIUS_K
+    mask_radius = cfg.ACTIVE.MASK_RADIUS_K
+    active_budget = cfg.ACTIVE.BUDGET / len(cfg.ACTIVE.SELECT_ITER)
+    uncertainty_type = cfg.ACTIVE.UNCERTAINTY
+    purity_type = cfg.ACTIVE.PURITY
+    K = cfg.ACTIVE.K
+
+    floating_region_score = FloatingRegionScore(in_channels=cfg.MODEL.NUM_CLASSES, size=2 * active_radius + 1,
+                                                purity_type=purity_type, K=K, curvature=cfg.MODEL.CURVATURE)
+    needs_embedding = (uncertainty_type in ["certainty", "hyperbolic"]
+                       or purity_type in ["hyper", "radius", "euc_norm"]
+                       or (uncertainty_type == "none" and cfg.MODEL.HYPER))
+
+    with torch.no_grad():
+        idx = 0
+        for tgt_data in tgt_epoch_loader:
+            tgt_input = tgt_data["img"].cuda(non_blocking=True)
+            path2mask, path2indicator = tgt_data["path_to_mask"], tgt_data["path_to_indicator"]
+            origin_mask, origin_label = tgt_data["origin_mask"], tgt_data["origin_label"]
+            origin_size = tgt_data["size"]
+            active_indicator, selected_indicator = tgt_data["active"], tgt_data["selected"]
+            if idx == 0:
+                feature_extractor.to(tgt_input.device)
+                classifier.to(tgt_input.device)
+            tgt_size = tgt_input.shape[-2:]
+            tgt_out, decoder_out = classifier(feature_extractor(tgt_input), size=tgt_size)
+
+            for i in range(len(origin_mask)):
+                active_mask = origin_mask[i].cuda(non_blocking=True)
+                ground_truth = origin_label[i].cuda(non_blocking=True)
+                size = (int(origin_size[i][0]), int(origin_size[i][1]))
+                active = active_indicator[i]
+                selected = selected_indicator[i]
+
+                output = F.interpolate(tgt_out[i:i + 1], size=size, mode="bilinear", align_corners=True)
+                emb = None
+                if needs_embedding:
+                    emb = decoder_out[i:i + 1]
+                    same = tuple(emb.shape[-2:]) == size
+                    if not (isinstance(emb, PoincareEmbedding) and same):
+                        # reference build.py:132-135: the embedding itself is up-sampled, THEN measured
+                        emb = F.interpolate(emb, size=size, mode="bilinear", align_corners=True)
+
+                score, _, _ = floating_region_score(output, decoder_out=emb, normalize=cfg.ACTIVE.NORMALIZE,
+                                                    unc_type=uncertainty_type, pur_type=purity_type,
+                                                    ground_truth=ground_truth)
+                score[active.to(score.device)] = -float("inf")
+                active_regions = math.ceil(size[0] * size[1] * active_budget / per_region_pixels)
+                score, active, selected, active_mask = select_pixels_to_label(
+                    score, active_regions, active_radius, mask_radius, active, selected, active_mask, ground_truth)
+
+                Image.fromarray(to_np_array(active_mask)).save(path2mask[i])
+                torch.save({"active": active, "selected": selected}, path2indicator[i])
+            idx += 1
+
+    feature_extractor.train()
+    classifier.train()

@@ -1,0 +1,501 @@
+// K4 -- fused backward of the Poincare-ball head (expmap0 + project + HyperMLR), CUDA-core fp32 path.
+//
+// The reference differentiates ~60 float64 autograd nodes (core/train_learners.py:238,362,457,557 through
+// core/utils/hyperbolic.py:28-39,120-184).  Here the forward contractions are recomputed from the raw
+// features and the whole epilogue is differentiated analytically per pixel:
+//     logit_k = f(n2, S_k, T_k ; pp_k, an_k, pa_k),  n2=|u|^2, S_k=<u,-P_k>, T_k=<u,A_k/|A_k|>
+//     du   = 2 u * sum_k G_k df/dn2 + sum_k (G_k df/dS_k) (-P_k) + (G_k df/dT_k) a_hat_k        (K4a, pass 2)
+//     dW   = sum_pix [gS ; gT] (x) u                                                             (K4b)
+//     dP, dA from dW and the per-class scalars d/dpp, d/dan, d/dpa by the chain rule             (K4c)
+// Reductions over pixels are two-stage with a fixed order (per-CTA partials, then one finalize block per
+// class), so gradients are bitwise reproducible for a given grid size.
+#include "common.cuh"
+#include "head_common.cuh"
+
+namespace halo {
+
+constexpr int BWD_THREADS = 256;
+constexpr int BWD_PIX = 2;
+constexpr int BWD_U = 4;
+constexpr int DW_THREADS = 128;   // each thread owns 2 channels of a 256-channel block
+constexpr int DW_PX = 32;         // pixels per shared-memory sub-tile
+
+struct BwdArgs {
+  const float* feat;
+  const float* dlogits;
+  const float* wpack;   // Wt[CPAD][2OP] + cls[4][OP]
+  float* dfeat;
+  float* G;             // [N][2OP][HW]  gS rows then gT rows
+  float* cls_part;      // [grid][3][OP]  per-CTA partial sums of d/dpp, d/dan, d/dpa
+  int N, C, CPAD, O, HW, tiles_per_img, total_tiles;
+  HeadConsts hc;
+};
+
+template <int OP, bool VEC>
+__global__ void __launch_bounds__(BWD_THREADS, 2) head_bwd_pix_kernel(const BwdArgs a) {
+  constexpr int KP = 2 * OP;
+  extern __shared__ __align__(16) float smem[];
+  float* sW = smem;
+  float* sCls = smem + (size_t)a.CPAD * KP;
+  float* sRed = sCls + 4 * OP;  // [warps][3][OP]
+  {
+    const int n4 = (a.CPAD * KP + 4 * OP) / 4;
+    const float4* src = reinterpret_cast<const float4*>(a.wpack);
+    float4* dst = reinterpret_cast<float4*>(smem);
+    for (int i = threadIdx.x; i < n4; i += BWD_THREADS) dst[i] = src[i];
+    for (int i = threadIdx.x; i < (BWD_THREADS / 32) * 3 * OP; i += BWD_THREADS) sRed[i] = 0.f;
+  }
+  __syncthreads();
+  const HeadConsts hc = a.hc;
+  const int HW = a.HW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+    const int n = tile / a.tiles_per_img;
+    const int p = (tile - n * a.tiles_per_img) * (BWD_THREADS * BWD_PIX) + threadIdx.x * BWD_PIX;
+    const float* base = a.feat + (size_t)n * a.C * HW;
+
+    float acc[BWD_PIX][KP];
+    float n2[BWD_PIX];
+#pragma unroll
+    for (int i = 0; i < BWD_PIX; ++i) {
+      n2[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < KP; ++k) acc[i][k] = 0.f;
+    }
+    // ---- pass 1: recompute the forward contractions ----
+    for (int cb = 0; cb < a.CPAD; cb += BWD_U) {
+      float cur[BWD_U][BWD_PIX];
+#pragma unroll
+      for (int j = 0; j < BWD_U; ++j) {
+        const int ch = cb + j;
+#pragma unroll
+        for (int i = 0; i < BWD_PIX; ++i) cur[j][i] = 0.f;
+        if (ch < a.C) {
+          if (VEC) {
+            if (p < HW) {
+              const float2 t = __ldg(reinterpret_cast<const float2*>(base + (size_t)ch * HW + p));
+              cur[j][0] = t.x;
+              cur[j][1] = t.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < BWD_PIX; ++i)
+              if (p + i < HW) cur[j][i] = __ldg(base + (size_t)ch * HW + p + i);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < BWD_U; ++j) {
+        const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)(cb + j) * KP);
+#pragma unroll
+        for (int i = 0; i < BWD_PIX; ++i) n2[i] = fmaf(cur[j][i], cur[j][i], n2[i]);
+#pragma unroll
+        for (int q = 0; q < KP / 4; ++q) {
+          const float4 w = w4[q];
+#pragma unroll
+          for (int i = 0; i < BWD_PIX; ++i) {
+            acc[i][4 * q + 0] = fmaf(cur[j][i], w.x, acc[i][4 * q + 0]);
+            acc[i][4 * q + 1] = fmaf(cur[j][i], w.y, acc[i][4 * q + 1]);
+            acc[i][4 * q + 2] = fmaf(cur[j][i], w.z, acc[i][4 * q + 2]);
+            acc[i][4 * q + 3] = fmaf(cur[j][i], w.w, acc[i][4 * q + 3]);
+          }
+        }
+      }
+    }
+
+    // ---- epilogue: analytic derivative of the head w.r.t. (n2, S_k, T_k) and the class scalars ----
+    float alpha[BWD_PIX];
+    float cpp[OP], can[OP], cpa[OP];  // this thread's contribution to d/dpp, d/dan, d/dpa
+#pragma unroll
+    for (int k = 0; k < OP; ++k) cpp[k] = can[k] = cpa[k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < BWD_PIX; ++i) {
+      const bool live = (p + i < HW);
+      const float nn = sqrtf(n2[i]);
+      const float nsafe = fmaxf(nn, 1e-15f);
+      const float sn = hc.s * nn;
+      const bool clipped = sn > hc.z_clip;
+      const float z = fminf(sn, hc.z_clip);
+      const float e = expf(-2.f * z);
+      const float t = clipped ? hc.t_clip : tanhf(z);
+      const float ope = 1.f + e;
+      const float omega = clipped ? hc.omega_clip : 4.f * e / (ope * ope);
+      const float gamma = t / (hc.s * nsafe);
+      const float t2 = t * t;
+      // derivatives of the per-pixel scalars w.r.t. n2
+      float dgam, dt2, dom;
+      if (clipped) {
+        dgam = -gamma / (2.f * fmaxf(n2[i], 1e-30f));
+        dt2 = 0.f;
+        dom = 0.f;
+      } else {
+        dgam = (z < 1e-3f) ? (-hc.c * (1.f / 3.f)) : (omega - gamma) / (2.f * fmaxf(n2[i], 1e-30f));
+        dt2 = t * hc.s * omega / nsafe;
+        dom = -t * omega * hc.s / nsafe;
+        if (nn < 1e-15f) { dt2 = hc.c; dom = -hc.c; }  // limits at the origin
+      }
+      float g_gamma = 0.f, g_t2 = 0.f, g_om = 0.f;
+#pragma unroll
+      for (int k = 0; k < OP; ++k) {
+        float gS = 0.f, gT = 0.f;
+        if (k < a.O) {
+          const float G = live ? __ldg(a.dlogits + ((size_t)n * a.O + k) * HW + p + i) : 0.f;
+          const float S = acc[i][k], T = acc[i][OP + k];
+          const float pp = sCls[k], an = sCls[OP + k], pa = sCls[2 * OP + k], Bk = sCls[3 * OP + k];
+          const float px = gamma * S, xa = gamma * T;
+          const float cpx2 = 2.f * hc.c * px;
+          const float Anum = 1.f + cpx2 + t2;
+          const float Draw = 1.f + cpx2 + hc.c * t2 * pp;
+          const bool dclamp = Draw < 1e-12f;
+          const float D = dclamp ? 1e-12f : Draw;
+          const float num = Bk * xa + Anum * pa;
+          const float bo = Bk * omega;
+          const float omc = bo / D;
+          float arg, a_num, a_bo, a_D;
+          if (omc >= hc.om_max) {
+            const float den = fmaxf(bo, 1e-12f * D);
+            arg = hc.two_s * num / den;
+            a_num = hc.two_s / den;
+            a_bo = -arg / den;
+            a_D = 0.f;
+          } else {
+            const float m = fmaxf(1.f - omc, 0.f) * (1.f / hc.c);
+            const float root = fmaxf(sqrtf(m), 1e-12f);
+            const float invD = 1.f / D;
+            arg = num * invD * (hc.out_scale / root);
+            a_num = invD * (hc.out_scale / root);
+            const float a_m = -arg / (2.f * root * root);   // d arg / d m  (through 1/root)
+            a_bo = a_m * (-invD / hc.c);
+            a_D = -arg * invD + a_m * (omc * invD / hc.c);
+          }
+          const float ash = asinhf(arg);
+          const float g = G * hc.two_over_s * an * rsqrtf(1.f + arg * arg);
+          const float g_num = g * a_num, g_bo = g * a_bo, g_D = dclamp ? 0.f : g * a_D;
+          float g_Bk = g_num * xa + g_bo * omega;
+          const float g_xa = g_num * Bk;
+          const float g_Anum = g_num * pa;
+          const float g_cpx2 = g_Anum + g_D;
+          g_t2 += g_Anum + g_D * hc.c * pp;
+          g_om += g_bo * Bk;
+          const float g_px = 2.f * hc.c * g_cpx2;
+          g_gamma += g_px * S + g_xa * T;
+          gS = g_px * gamma;
+          gT = g_xa * gamma;
+          cpp[k] += g_D * hc.c * t2 - hc.c * g_Bk;
+          can[k] += G * hc.two_over_s * ash;
+          cpa[k] += g_num * Anum;
+        }
+        acc[i][k] = gS;
+        acc[i][OP + k] = gT;
+      }
+      alpha[i] = 2.f * (g_gamma * dgam + g_t2 * dt2 + g_om * dom);
+    }
+    // per-class scalars: fixed-order warp reduction, then this warp's shared-memory slot
+#pragma unroll
+    for (int k = 0; k < OP; ++k) {
+      float v0 = cpp[k], v1 = can[k], v2 = cpa[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+      }
+      if (lane == 0) {
+        sRed[(warp * 3 + 0) * OP + k] += v0;
+        sRed[(warp * 3 + 1) * OP + k] += v1;
+        sRed[(warp * 3 + 2) * OP + k] += v2;
+      }
+    }
+    // G planes for the weight-gradient GEMM
+    if (p < HW) {
+#pragma unroll
+      for (int k = 0; k < KP; ++k) {
+        float* row = a.G + ((size_t)n * KP + k) * HW + p;
+        if (VEC) *reinterpret_cast<float2*>(row) = make_float2(acc[0][k], acc[1][k]);
+        else {
+          row[0] = acc[0][k];
+          if (p + 1 < HW) row[1] = acc[1][k];
+        }
+      }
+    }
+    // ---- pass 2: du = alpha*u + [gS gT] . Wt^T ----
+    float* dbase = a.dfeat + (size_t)n * a.C * HW;
+    for (int ch = 0; ch < a.C; ++ch) {
+      float u[BWD_PIX] = {0.f, 0.f};
+      if (VEC) {
+        if (p < HW) {
+          const float2 t = __ldg(reinterpret_cast<const float2*>(base + (size_t)ch * HW + p));
+          u[0] = t.x;
+          u[1] = t.y;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < BWD_PIX; ++i)
+          if (p + i < HW) u[i] = __ldg(base + (size_t)ch * HW + p + i);
+      }
+      float d[BWD_PIX];
+#pragma unroll
+      for (int i = 0; i < BWD_PIX; ++i) d[i] = alpha[i] * u[i];
+      const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)ch * KP);
+#pragma unroll
+      for (int q = 0; q < KP / 4; ++q) {
+        const float4 w = w4[q];
+#pragma unroll
+        for (int i = 0; i < BWD_PIX; ++i) {
+          d[i] = fmaf(acc[i][4 * q + 0], w.x, d[i]);
+          d[i] = fmaf(acc[i][4 * q + 1], w.y, d[i]);
+          d[i] = fmaf(acc[i][4 * q + 2], w.z, d[i]);
+          d[i] = fmaf(acc[i][4 * q + 3], w.w, d[i]);
+        }
+      }
+      if (VEC) {
+        if (p < HW) __stcs(reinterpret_cast<float2*>(dbase + (size_t)ch * HW + p), make_float2(d[0], d[1]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < BWD_PIX; ++i)
+          if (p + i < HW) dbase[(size_t)ch * HW + p + i] = d[i];
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * OP; i += BWD_THREADS) {
+    float s = 0.f;
+    for (int w = 0; w < BWD_THREADS / 32; ++w) s += sRed[w * 3 * OP + i];
+    a.cls_part[(size_t)blockIdx.x * 3 * OP + i] = s;
+  }
+}
+
+// K4b: dW[k][c] = sum_pix G[k][pix] * u[c][pix].  Persistent CTAs, register accumulators, one partial per CTA.
+template <int OP>
+__global__ void __launch_bounds__(DW_THREADS) head_bwd_dw_kernel(const float* __restrict__ feat, const float* __restrict__ G,
+                                                                  float* __restrict__ dw_part, int N, int C, int HW,
+                                                                  int cblocks, long long total_units) {
+  constexpr int KP = 2 * OP;
+  __shared__ float sU[256][DW_PX + 1];
+  __shared__ __align__(16) float sG[DW_PX][KP];
+  const int tid = threadIdx.x;
+  // a "unit" = (channel block of 256, image, 32-pixel strip); units of one channel block are contiguous per CTA
+  const int strips = (HW + DW_PX - 1) / DW_PX;
+  for (int cbk = 0; cbk < cblocks; ++cbk) {
+    float acc[2][KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) acc[0][k] = acc[1][k] = 0.f;
+    const int c0 = cbk * 256;
+    for (long long unit = blockIdx.x; unit < (long long)N * strips; unit += gridDim.x) {
+      const int n = (int)(unit / strips);
+      const int p0 = (int)(unit - (long long)n * strips) * DW_PX;
+      __syncthreads();
+      // u tile: warp w loads channels w, w+4, ... ; lane = pixel (coalesced 128 B rows)
+      for (int r = tid >> 5; r < 256; r += DW_THREADS / 32) {
+        const int ch = c0 + r, px = p0 + (tid & 31);
+        sU[r][tid & 31] = (ch < C && px < HW) ? __ldg(feat + ((size_t)n * C + ch) * HW + px) : 0.f;
+      }
+      for (int i = tid; i < DW_PX * KP; i += DW_THREADS) {
+        const int k = i / DW_PX, j = i - k * DW_PX;
+        const int px = p0 + j;
+        sG[j][k] = (px < HW) ? __ldg(G + ((size_t)n * KP + k) * HW + px) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int j = 0; j < DW_PX; ++j) {
+        const float u0 = sU[tid][j], u1 = sU[tid + 128][j];
+        const float4* g4 = reinterpret_cast<const float4*>(&sG[j][0]);
+#pragma unroll
+        for (int q = 0; q < KP / 4; ++q) {
+          const float4 g = g4[q];
+          acc[0][4 * q + 0] = fmaf(g.x, u0, acc[0][4 * q + 0]);
+          acc[0][4 * q + 1] = fmaf(g.y, u0, acc[0][4 * q + 1]);
+          acc[0][4 * q + 2] = fmaf(g.z, u0, acc[0][4 * q + 2]);
+          acc[0][4 * q + 3] = fmaf(g.w, u0, acc[0][4 * q + 3]);
+          acc[1][4 * q + 0] = fmaf(g.x, u1, acc[1][4 * q + 0]);
+          acc[1][4 * q + 1] = fmaf(g.y, u1, acc[1][4 * q + 1]);
+          acc[1][4 * q + 2] = fmaf(g.z, u1, acc[1][4 * q + 2]);
+          acc[1][4 * q + 3] = fmaf(g.w, u1, acc[1][4 * q + 3]);
+        }
+      }
+    }
+    // partial [grid][KP][CP] with CP = cblocks*256
+    float* out = dw_part + (size_t)blockIdx.x * KP * (cblocks * 256);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      out[(size_t)k * (cblocks * 256) + c0 + tid] = acc[0][k];
+      out[(size_t)k * (cblocks * 256) + c0 + tid + 128] = acc[1][k];
+    }
+  }
+}
+
+// K4c: fixed-order reduction of the per-CTA partials + chain rule to dP, dA.  One block per class.
+__global__ void head_bwd_finalize_kernel(const float* __restrict__ P, const float* __restrict__ A,
+                                         const float* __restrict__ dw_part, int dw_grid, const float* __restrict__ cls_part,
+                                         int cls_grid, float* __restrict__ dP, float* __restrict__ dA, int O, int OP, int C,
+                                         int CP) {
+  const int k = blockIdx.x;
+  const int KP = 2 * OP;
+  __shared__ double red[32];
+  __shared__ double s_an2, s_dot;
+  __shared__ float s_cls[3];
+  if (threadIdx.x < 3) {
+    float s = 0.f;
+    for (int g = 0; g < cls_grid; ++g) s += cls_part[((size_t)g * 3 + threadIdx.x) * OP + k];
+    s_cls[threadIdx.x] = s;
+  }
+  // |A_k|^2
+  double aa = 0.0;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const double v = (double)A[(size_t)k * C + ch];
+    aa += v * v;
+  }
+  for (int o = 16; o > 0; o >>= 1) aa += __shfl_xor_sync(0xffffffffu, aa, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = aa;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    s_an2 = s;
+  }
+  __syncthreads();
+  const double an = sqrt(s_an2);
+  const double den = an > 1e-12 ? an : 1e-12;
+  const float g_pp = s_cls[0], g_an = s_cls[1], g_pa = s_cls[2];
+  // d a_hat (total) and its projection on a_hat
+  double dot = 0.0;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float sT = 0.f;
+    for (int g = 0; g < dw_grid; ++g) sT += dw_part[((size_t)g * KP + OP + k) * CP + ch];
+    const double ahat = (double)A[(size_t)k * C + ch] / den;
+    const double dah = (double)sT + (double)g_pa * (-(double)P[(size_t)k * C + ch]);
+    dot += dah * ahat;
+  }
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    s_dot = s;
+  }
+  __syncthreads();
+  const double pdot = s_dot;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float sS = 0.f, sT = 0.f;
+    for (int g = 0; g < dw_grid; ++g) {
+      sS += dw_part[((size_t)g * KP + k) * CP + ch];
+      sT += dw_part[((size_t)g * KP + OP + k) * CP + ch];
+    }
+    const double p = (double)P[(size_t)k * C + ch];
+    const double ahat = (double)A[(size_t)k * C + ch] / den;
+    const double dq = (double)sS + (double)g_pa * ahat;      // d/dq_k, q = -P
+    const double dah = (double)sT + (double)g_pa * (-p);     // d/da_hat_k
+    dP[(size_t)k * C + ch] = (float)(-dq + 2.0 * p * (double)g_pp);
+    dA[(size_t)k * C + ch] = (float)((dah - pdot * ahat) / den + (double)g_an * ahat);
+  }
+}
+
+}  // namespace halo
+
+using namespace halo;
+
+static int bwd_grids(int N, int HW, int* pix_grid, int* dw_grid) {
+  const int tiles = ((HW + BWD_THREADS * BWD_PIX - 1) / (BWD_THREADS * BWD_PIX)) * N;
+  int g = sm_count() * 2;
+  if (g > tiles) g = tiles;
+  *pix_grid = g;
+  const long long units = (long long)N * ((HW + DW_PX - 1) / DW_PX);
+  long long d = (long long)sm_count() * 4;
+  if (d > units) d = units;
+  *dw_grid = (int)d;
+  return 0;
+}
+
+extern "C" size_t halo_head_bwd_workspace_bytes(int N, int C, int O, int H, int W) {
+  if (N <= 0 || C <= 0 || O <= 0 || H <= 0 || W <= 0) return 0;
+  const int OP = head_op_pad(O), KP = 2 * OP, CPAD = round_up(C, 4), CP = round_up(C, 256);
+  int pg, dg;
+  bwd_grids(N, H * W, &pg, &dg);
+  size_t b = ((size_t)CPAD * KP + 4 * OP) * 4;          // packed parameters
+  b = (b + 255) / 256 * 256;
+  b += (size_t)N * KP * H * W * 4;                       // G planes
+  b = (b + 255) / 256 * 256;
+  b += (size_t)pg * 3 * OP * 4;                          // class-scalar partials
+  b = (b + 255) / 256 * 256;
+  b += (size_t)dg * KP * CP * 4;                         // dW partials
+  return b + 256;
+}
+
+template <int OP>
+static int launch_bwd(const BwdArgs& a, bool vec, size_t smem, int pix_grid, int dw_grid, const float* feat, float* dwp,
+                      int cblocks, cudaStream_t st) {
+  if (vec) {
+    HALO_CUDA(cudaFuncSetAttribute(head_bwd_pix_kernel<OP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_bwd_pix_kernel<OP, true><<<pix_grid, BWD_THREADS, smem, st>>>(a);
+  } else {
+    HALO_CUDA(cudaFuncSetAttribute(head_bwd_pix_kernel<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_bwd_pix_kernel<OP, false><<<pix_grid, BWD_THREADS, smem, st>>>(a);
+  }
+  int rc = launch_status("head_bwd_pix_kernel");
+  if (rc) return rc;
+  head_bwd_dw_kernel<OP><<<dw_grid, DW_THREADS, 0, st>>>(feat, a.G, dwp, a.N, a.C, a.HW, cblocks,
+                                                         (long long)a.N * ((a.HW + DW_PX - 1) / DW_PX));
+  return launch_status("head_bwd_dw_kernel");
+}
+
+extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, float c, const float* dlogits, float* dfeat,
+                             float* dP, float* dA, int N, int C, int O, int H, int W, void* ws, size_t ws_bytes,
+                             halo_stream_t stream) {
+  HALO_CHECK_ARG(feat && P && A && dlogits && dfeat && dP && dA, "halo_head_bwd: NULL pointer");
+  HALO_CHECK_ARG(N > 0 && C > 0 && O > 0 && H > 0 && W > 0 && c > 0.f, "halo_head_bwd: bad dims / curvature");
+  if (O > 32) {
+    set_error("halo_head_bwd: num_classes %d > 32 not compiled", O);
+    return HALO_ERR_UNSUPPORTED;
+  }
+  const size_t need = halo_head_bwd_workspace_bytes(N, C, O, H, W);
+  if (!ws || ws_bytes < need) {
+    set_error("halo_head_bwd: workspace %zu < %zu bytes", ws_bytes, need);
+    return HALO_ERR_WORKSPACE;
+  }
+  const int OP = head_op_pad(O), KP = 2 * OP, CPAD = round_up(C, 4), CP = round_up(C, 256), HW = H * W;
+  int pix_grid, dw_grid;
+  bwd_grids(N, HW, &pix_grid, &dw_grid);
+  unsigned char* w8 = (unsigned char*)ws;
+  size_t off = 0;
+  float* wpack = (float*)(w8 + off);
+  off += ((size_t)CPAD * KP + 4 * OP) * 4; off = (off + 255) / 256 * 256;
+  float* G = (float*)(w8 + off);
+  off += (size_t)N * KP * HW * 4; off = (off + 255) / 256 * 256;
+  float* cls_part = (float*)(w8 + off);
+  off += (size_t)pix_grid * 3 * OP * 4; off = (off + 255) / 256 * 256;
+  float* dw_part = (float*)(w8 + off);
+
+  cudaStream_t st = (cudaStream_t)stream;
+  head_pack_kernel<<<OP, 128, 0, st>>>(P, A, c, O, OP, C, CPAD, wpack, nullptr, 0);
+  int rc = launch_status("head_pack_kernel");
+  if (rc) return rc;
+  const size_t smem = ((size_t)CPAD * KP + 4 * OP + (BWD_THREADS / 32) * 3 * OP) * 4;
+  if (smem > 200 * 1024) {
+    set_error("halo_head_bwd: C=%d x O=%d class parameters exceed the shared-memory tile", C, O);
+    return HALO_ERR_UNSUPPORTED;
+  }
+  BwdArgs a;
+  a.feat = feat; a.dlogits = dlogits; a.wpack = wpack; a.dfeat = dfeat; a.G = G; a.cls_part = cls_part;
+  a.N = N; a.C = C; a.CPAD = CPAD; a.O = O; a.HW = HW;
+  a.tiles_per_img = (HW + BWD_THREADS * BWD_PIX - 1) / (BWD_THREADS * BWD_PIX);
+  a.total_tiles = a.tiles_per_img * N;
+  a.hc = make_head_consts(c);
+  const bool vec = (HW % 2 == 0) && ((uintptr_t)feat % 8 == 0) && ((uintptr_t)dfeat % 8 == 0);
+  const int cblocks = CP / 256;
+  switch (OP) {
+    case 4: rc = launch_bwd<4>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+    case 8: rc = launch_bwd<8>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+    case 12: rc = launch_bwd<12>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+    case 16: rc = launch_bwd<16>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+    case 20: rc = launch_bwd<20>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+    case 24: rc = launch_bwd<24>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+    case 28: rc = launch_bwd<28>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+    default: rc = launch_bwd<32>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+  }
+  if (rc) return rc;
+  head_bwd_finalize_kernel<<<O, 256, 0, st>>>(P, A, dw_part, dw_grid, cls_part, pix_grid, dP, dA, O, OP, C, CP);
+  return launch_status("head_bwd_finalize_kernel");
+}

@@ -1,0 +1,168 @@
+"""Floating-region acquisition score -- B200 mirror of the reference's `core/active/floating_region.py`.
+
+`FloatingRegionScore` keeps the reference's constructor and forward signature (:26-29, :129-137) and its
+quirks (entropy / log 19 whatever the class count; zero-padded box SUM; `count` = window population only for
+the histogram purities; a module BUILT for "hyper" uses a 3x3 purity window whatever `size`, :54-55).
+All arithmetic is `halo_logits_stats` + `halo_ball_norm` / the fused head's radius + `halo_score`.
+Results are fp32 (the reference returns an fp64 score in "radius" mode because its radius is fp64).
+"""
+import torch
+import torch.nn as nn
+
+from . import _native as nat
+from .hyperbolic import HyperMapper, PoincareEmbedding
+
+_HIST_PURITIES = ("ripu", "oracle_ripu", "hyper")
+_KNOWN_PURITIES = ("ripu", "oracle_ripu", "hyper", "none", "radius", "euc_norm")
+
+
+def _reference_cfg(path, default):
+    """Read a key of the reference's global yacs cfg when running inside its tree (floating_region.py:8,39,68)."""
+    try:
+        from core.configs import cfg  # type: ignore
+
+        node = cfg
+        for part in path.split("."):
+            node = getattr(node, part)
+        return node
+    except Exception:
+        return default
+
+
+def score_planes(pixunc, radius, radius_stats, label, active, *, unc_mode, pur_mode, normalize, k, pk, n_bins,
+                 want_impurity=True):
+    """Batched `halo_score` on device planes (N,H,W).  Returns (score, impurity|None, uncertainty)."""
+    lib = nat.load()
+    ref = pixunc if pixunc is not None else radius
+    if ref is None:
+        raise ValueError("score_planes: need at least one input plane")
+    N, H, W = ref.shape
+    dev = ref.device
+    score = torch.empty((N, H, W), dtype=torch.float32, device=dev)
+    unc = torch.empty((N, H, W), dtype=torch.float32, device=dev)
+    need_imp = want_impurity or pur_mode in (nat.PUR_LABEL_HIST, nat.PUR_RADIUS_BINS)
+    imp = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need_imp else None
+    ws = nat.workspace.get(dev, "score", lib.halo_score_workspace_bytes(N))
+    with torch.cuda.device(dev):
+        rc = lib.halo_score(nat.ptr(pixunc), nat.ptr(radius), nat.ptr(radius_stats), nat.ptr(label), nat.ptr(active),
+                            unc_mode, pur_mode, 1 if normalize else 0, k, pk, n_bins, nat.ptr(score), nat.ptr(imp),
+                            nat.ptr(unc), N, H, W, nat.ptr(ws), ws.numel(), nat.stream_of(ref))
+    nat.check(rc, "halo_score")
+    return score, imp, unc
+
+
+def modes_for(unc_type, pur_type):
+    """Map the reference's strings to the kernel modes (floating_region.py:70-92,158-202)."""
+    if pur_type not in _KNOWN_PURITIES:
+        raise NotImplementedError("Error: purity type '{}' not implemented".format(pur_type))
+    if unc_type == "pixel_entropy":
+        unc_mode, pixunc_mode = nat.UNC_PIXEL, "entropy"
+    elif unc_type == "entropy":
+        unc_mode, pixunc_mode = nat.UNC_BOXSUM, "entropy"
+    elif unc_type == "oracle_acc":
+        unc_mode, pixunc_mode = nat.UNC_BOXSUM, "one_minus_pgt"
+    else:  # "none" and unknown strings ("hyperbolic", "certainty"): zeros (box-summed zeros are zeros)
+        unc_mode, pixunc_mode = nat.UNC_ZERO, "entropy"
+    if pur_type == "ripu":
+        pur_mode, label_mode = nat.PUR_LABEL_HIST, "argmax"
+    elif pur_type == "oracle_ripu":
+        pur_mode, label_mode = nat.PUR_LABEL_HIST, "gt_filled"
+    elif pur_type == "hyper":
+        pur_mode, label_mode = nat.PUR_RADIUS_BINS, "argmax"
+    elif pur_type == "none":
+        pur_mode, label_mode = nat.PUR_ZERO, "argmax"
+    else:
+        pur_mode, label_mode = nat.PUR_NORM, "argmax"
+    norm_mode = "euclid" if pur_type == "euc_norm" else "radius"
+    return unc_mode, pixunc_mode, pur_mode, label_mode, norm_mode
+
+
+class FloatingRegionScore(nn.Module):
+    def __init__(self, in_channels=19, padding_mode="zeros", size=33, purity_type=None, K=100, curvature=None):
+        """purity window: size x size (3 x 3 when built for 'hyper'); entropy window: size x size."""
+        super(FloatingRegionScore, self).__init__()
+        self.in_channels = in_channels
+        assert size % 2 == 1, "error size"
+        if padding_mode != "zeros":
+            raise NotImplementedError("FloatingRegionScore: only zero padding is implemented (the reference default)")
+        if purity_type is None:
+            purity_type = _reference_cfg("ACTIVE.PURITY", "hyper")
+        self.size = size
+        self.purity_size = size
+        self.purity_type = purity_type
+        if purity_type == "hyper":
+            self.K, self.purity_size = K, 3  # reference :54-55
+        if curvature is None:
+            curvature = _reference_cfg("MODEL.CURVATURE", 1.0)
+        self.mapper = HyperMapper(c=curvature)
+
+    def _radius_plane(self, decoder_out, norm_mode, want_stats):
+        """(N,H,W) radius / euclidean-norm plane (+ per-image min/max) of the embedding."""
+        c = self.mapper.c
+        if isinstance(decoder_out, PoincareEmbedding):
+            if norm_mode == "radius":
+                r = decoder_out.poincare_radius()
+                return r, (decoder_out.radius_stats() if want_stats else None)
+            return decoder_out.poincare_radius("euclid"), None
+        lib = nat.load()
+        x = nat.require_cuda(decoder_out, "decoder_out")
+        if x.dtype not in (torch.float32, torch.float64):
+            x = x.float()
+        x = x.contiguous()
+        N, C, H, W = x.shape
+        out = torch.empty((N, H, W), dtype=torch.float32, device=x.device)
+        stats = torch.empty((N, 4), dtype=torch.float32, device=x.device) if want_stats else None
+        with torch.cuda.device(x.device):
+            rc = lib.halo_ball_norm(nat.ptr(x), 1 if x.dtype == torch.float64 else 0, float(c),
+                                    nat.NORM_EUCLID if norm_mode == "euclid" else nat.NORM_RADIUS, nat.ptr(out),
+                                    nat.ptr(stats), N, C, H, W, nat.stream_of(x))
+        nat.check(rc, "halo_ball_norm")
+        return out, stats
+
+    def forward(self, logit: torch.Tensor, decoder_out=None, unc_type: str = None, pur_type: str = None,
+                normalize: bool = False, ground_truth=None):
+        """Compute region score, impurity and uncertainty (reference :129-217).
+
+        logit: (1,O,H,W) (a batch (N,O,H,W) is accepted as an extension and returns (N,H,W) maps);
+        decoder_out: PoincareEmbedding or (N,C,H,W) tensor on the ball (needed by 'radius'/'hyper'/'euc_norm').
+        Returns (score, region_impurity, prediction_uncertainty), each (H,W)."""
+        lib = nat.load()
+        nat.require_cuda(logit, "logit")
+        unc_mode, pixunc_mode, pur_mode, label_mode, norm_mode = modes_for(unc_type, pur_type)
+        if pur_type in ("ripu", "oracle_ripu") and self.purity_type == "hyper":
+            raise RuntimeError("FloatingRegionScore built for 'hyper' purity cannot score '%s' "
+                               "(the reference's purity_conv has K channels)" % pur_type)
+        if pur_type == "hyper" and self.purity_type != "hyper":
+            raise AttributeError("'FloatingRegionScore' object has no attribute 'K' (module was not built for 'hyper')")
+        logit = logit.float().contiguous()
+        N, O, H, W = logit.shape
+        dev = logit.device
+        gt8 = None
+        if pixunc_mode == "one_minus_pgt" or label_mode == "gt_filled":
+            if ground_truth is None:
+                raise ValueError("ground_truth is required by unc_type/pur_type '%s'/'%s'" % (unc_type, pur_type))
+            gt8 = nat.require_cuda(ground_truth, "ground_truth").to(torch.uint8).reshape(N, H, W).contiguous()
+        need_pixunc = unc_mode != nat.UNC_ZERO
+        need_label = pur_mode == nat.PUR_LABEL_HIST
+        pixunc = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need_pixunc else None
+        label = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if need_label else None
+        if need_pixunc or need_label:
+            with torch.cuda.device(dev):
+                rc = lib.halo_logits_stats(nat.ptr(logit), nat.ptr(gt8), nat.PIXUNC_ONE_MINUS_PGT if pixunc_mode == "one_minus_pgt" else nat.PIXUNC_ENTROPY,
+                                           nat.LABEL_GT_FILLED if label_mode == "gt_filled" else nat.LABEL_ARGMAX,
+                                           nat.ptr(pixunc), nat.ptr(label), N, O, H, W, nat.stream_of(logit))
+            nat.check(rc, "halo_logits_stats")
+        radius = stats = None
+        if pur_mode in (nat.PUR_NORM, nat.PUR_RADIUS_BINS):
+            if decoder_out is None:
+                raise ValueError("decoder_out is required by pur_type '%s'" % pur_type)
+            radius, stats = self._radius_plane(decoder_out, norm_mode, pur_mode == nat.PUR_RADIUS_BINS)
+        n_bins = self.K if pur_mode == nat.PUR_RADIUS_BINS else self.in_channels
+        if pixunc is None and radius is None:  # "none"/"none": the kernel still needs a shape carrier
+            pixunc = torch.zeros((N, H, W), dtype=torch.float32, device=dev)
+        score, imp, unc = score_planes(pixunc, radius, stats, label, None, unc_mode=unc_mode, pur_mode=pur_mode,
+                                       normalize=normalize, k=self.size, pk=self.purity_size, n_bins=n_bins,
+                                       want_impurity=True)
+        if N == 1:
+            return score[0], imp[0], unc[0]
+        return score, imp, unc

@@ -1,0 +1,159 @@
+"""Device-resident, image-sharded acquisition round (the hot path end to end).
+
+`acquire_batch` runs K1 (fused head) -> K2 (region score) -> K3 (budgeted selection) on a batch of images
+that is already in HBM, with no host synchronisation.  `acquire_pool` shards a pool of images over the ranks
+of a torch.distributed job (one process per GPU; images are independent units -- score normalisation,
+budget and suppression are all per image: floating_region.py:22-23, build.py:148-160) and all-gathers the
+per-image pick counts and masks at the end; that all-gather is the only collective on the path.
+The reference runs this loop on rank 0 alone, one image at a time (train_learners.py:308-322, build.py:92).
+"""
+import math
+from dataclasses import dataclass
+
+import torch
+
+from . import _native as nat
+from .active import select_planes
+from .floating_region import modes_for, score_planes
+from .hyperbolic import head_forward
+
+
+@dataclass
+class AcquisitionConfig:
+    """The cfg keys the hot path reads (build.py:75-81,140; floating_region.py:68; defaults.py:66-79)."""
+    num_classes: int = 19
+    curvature: float = 1.0
+    radius_k: int = 1            # ACTIVE.RADIUS_K  -> (2k+1)^2 region, active_radius
+    mask_radius_k: int = 5       # ACTIVE.MASK_RADIUS_K
+    budget: float = 0.05         # ACTIVE.BUDGET (total, over all rounds)
+    n_rounds: int = 1            # len(ACTIVE.SELECT_ITER); per-round budget = budget / n_rounds (build.py:78)
+    uncertainty: str = "entropy"
+    purity: str = "radius"
+    K: int = 100
+    normalize: bool = True
+
+    @classmethod
+    def from_cfg(cls, cfg):
+        return cls(num_classes=cfg.MODEL.NUM_CLASSES, curvature=cfg.MODEL.CURVATURE, radius_k=cfg.ACTIVE.RADIUS_K,
+                   mask_radius_k=cfg.ACTIVE.MASK_RADIUS_K, budget=cfg.ACTIVE.BUDGET,
+                   n_rounds=len(cfg.ACTIVE.SELECT_ITER), uncertainty=cfg.ACTIVE.UNCERTAINTY,
+                   purity=cfg.ACTIVE.PURITY, K=cfg.ACTIVE.K, normalize=cfg.ACTIVE.NORMALIZE)
+
+    def regions_per_image(self, h, w):
+        per_region = (2 * self.radius_k + 1) ** 2
+        return math.ceil(h * w * (self.budget / self.n_rounds) / per_region)  # build.py:148-150
+
+
+def acquire_batch(feat, P, A, cfg, gt, active, selected, active_mask, *, want_score=False, want_picks=False):
+    """One acquisition step on a resident batch.
+
+    feat (B,C,H,W) fp32 raw decoder features; gt/active/selected/active_mask (B,H,W) uint8, the last three are
+    updated IN PLACE exactly as select_pixels_to_label does.  Returns dict(n_picked (B,) int32 [, score, picks])."""
+    B, C, H, W = feat.shape
+    unc_mode, pixunc_mode, pur_mode, label_mode, norm_mode = modes_for(cfg.uncertainty, cfg.purity)
+    need_pixunc = unc_mode != nat.UNC_ZERO
+    need_label = pur_mode == nat.PUR_LABEL_HIST
+    need_radius = pur_mode in (nat.PUR_NORM, nat.PUR_RADIUS_BINS)
+    need_gt = pixunc_mode == "one_minus_pgt" or label_mode == "gt_filled"
+    res = head_forward(feat, P, A, cfg.curvature, kind="tangent", want_logits=False, want_radius=need_radius,
+                       want_pixunc=need_pixunc, want_label=need_label, want_stats=pur_mode == nat.PUR_RADIUS_BINS,
+                       gt=gt if need_gt else None, pixunc_mode=pixunc_mode, label_mode=label_mode, norm_mode=norm_mode)
+    pixunc = res["pixunc"]
+    if pixunc is None and res["radius"] is None:
+        pixunc = torch.zeros((B, H, W), dtype=torch.float32, device=feat.device)
+    k = 2 * cfg.radius_k + 1
+    pk = 3 if cfg.purity == "hyper" else k
+    n_bins = cfg.K if pur_mode == nat.PUR_RADIUS_BINS else cfg.num_classes
+    score, _, _ = score_planes(pixunc, res["radius"], res["stats"], res["label"], active, unc_mode=unc_mode,
+                               pur_mode=pur_mode, normalize=cfg.normalize, k=k, pk=pk, n_bins=n_bins,
+                               want_impurity=False)
+    out = {}
+    if want_score:
+        out["score"] = score.clone()
+    n_regions = cfg.regions_per_image(H, W)
+    n_picked, picks = select_planes(score, active, selected, active_mask, gt, n_regions, cfg.radius_k,
+                                    cfg.mask_radius_k, want_picks=want_picks)
+    out["n_picked"] = n_picked
+    out["n_regions"] = n_regions
+    if want_picks:
+        out["picks"] = picks
+    return out
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous block of image indices owned by `rank` (last blocks may be one shorter)."""
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def acquire_pool(provider, n_images, P, A, cfg, *, batch_size=8, group=None, gather=True, device=None):
+    """Run one acquisition round over a pool of `n_images` images sharded by image over the ranks of `group`.
+
+    provider(lo, hi) -> dict(feat (b,C,H,W) fp32, gt, active, selected, active_mask (b,H,W) uint8), tensors on
+    this rank's device for global image indices [lo, hi).  Returns dict with this rank's planes and, when
+    `gather`, the all-gathered `n_picked` (n_images,) and `active_mask` (n_images,H,W) on every rank."""
+    import torch.distributed as dist
+
+    distributed = dist.is_available() and dist.is_initialized()
+    rank = dist.get_rank(group) if distributed else 0
+    world = dist.get_world_size(group) if distributed else 1
+    lo, hi = shard_range(n_images, rank, world)
+    counts, masks, actives, selecteds = [], [], [], []
+    for b0 in range(lo, hi, batch_size):
+        b1 = min(b0 + batch_size, hi)
+        item = provider(b0, b1)
+        res = acquire_batch(item["feat"], P, A, cfg, item["gt"], item["active"], item["selected"], item["active_mask"])
+        counts.append(res["n_picked"])
+        masks.append(item["active_mask"])
+        actives.append(item["active"])
+        selecteds.append(item["selected"])
+    out = {"rank": rank, "world": world, "range": (lo, hi)}
+    if counts:
+        out["n_picked_local"] = torch.cat(counts)
+        out["active_mask_local"] = torch.cat(masks)
+        out["active_local"] = torch.cat(actives)
+        out["selected_local"] = torch.cat(selecteds)
+    if gather:
+        out.update(gather_round(out.get("n_picked_local"), out.get("active_mask_local"), n_images, group=group,
+                                device=device))
+    return out
+
+
+def gather_round(n_picked_local, mask_local, n_images, *, group=None, device=None):
+    """All-gather the per-shard pick counts and masks (the only collective on the path).
+
+    Shards are padded to the largest shard so a single all_gather_into_tensor per tensor suffices; works on
+    NCCL (CUDA tensors) and gloo (CPU tensors, used by the world_size-2 CPU tests)."""
+    import torch.distributed as dist
+
+    distributed = dist.is_available() and dist.is_initialized()
+    if not distributed:
+        return {"n_picked": n_picked_local, "active_mask": mask_local}
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    per = (n_images + world - 1) // world
+    lo, hi = shard_range(n_images, rank, world)
+    n_local = hi - lo
+    if mask_local is not None:
+        dev, hw = mask_local.device, tuple(mask_local.shape[1:])
+    else:
+        dev, hw = torch.device(device or "cpu"), None
+    # agree on the plane shape (a rank may own zero images when world > n_images)
+    shape_t = torch.tensor(list(hw) if hw else [0, 0], dtype=torch.int64, device=dev)
+    dist.all_reduce(shape_t, op=dist.ReduceOp.MAX, group=group)
+    hw = (int(shape_t[0]), int(shape_t[1]))
+    cnt_pad = torch.zeros((per,), dtype=torch.int32, device=dev)
+    msk_pad = torch.full((per,) + hw, 255, dtype=torch.uint8, device=dev)
+    if n_local:
+        cnt_pad[:n_local] = n_picked_local
+        msk_pad[:n_local] = mask_local
+    cnt_all = torch.empty((world * per,), dtype=torch.int32, device=dev)
+    msk_all = torch.empty((world * per,) + hw, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(cnt_all, cnt_pad, group=group)
+    dist.all_gather_into_tensor(msk_all, msk_pad, group=group)
+    keep = []
+    for r in range(world):
+        a, b = shard_range(n_images, r, world)
+        keep.extend(range(r * per, r * per + (b - a)))
+    keep_t = torch.tensor(keep, dtype=torch.long, device=dev)
+    return {"n_picked": cnt_all.index_select(0, keep_t), "active_mask": msk_all.index_select(0, keep_t)}

@@ -1,0 +1,146 @@
+/*
+ * halo_b200.h -- C ABI of libhalo_sm100.so: the B200 (sm_100a) implementation of HALO's per-pixel
+ * hyperbolic hot path (Poincare-ball classifier head + active-learning acquisition pass).
+ *
+ * Plain C types, raw DEVICE pointers and a CUDA stream handle only; no torch / C++ types cross this
+ * boundary.  Every entry point enqueues on the caller's stream and returns without synchronising.
+ * The library owns no tensor memory: outputs and scratch ("workspace") are caller-provided, sized by
+ * the matching *_workspace_bytes() query.  Return value: 0 on success, negative halo_status otherwise;
+ * halo_last_error() returns a thread-local human-readable message for the last failure.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference
+ * checkout paolomandica/HALO).  The reference has no FFI of its own (it is pure PyTorch); the
+ * binding a maintainer would add is the ctypes stub shown in INTEGRATION.md.
+ *
+ * Layouts: all image-shaped tensors are contiguous NCHW / NHW, channel reduction on dim=1 exactly as
+ * the reference (core/models/classifier.py:553, core/utils/hyperbolic.py:136).
+ */
+#ifndef HALO_B200_H
+#define HALO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HALO_ABI_VERSION 1
+
+typedef void* halo_stream_t; /* cudaStream_t / CUstream of the caller; NULL = legacy default stream */
+
+typedef enum {
+  HALO_OK = 0,
+  HALO_ERR_BAD_ARG = -1,     /* NULL / non-positive dims / inconsistent options */
+  HALO_ERR_UNSUPPORTED = -2, /* legal request outside the compiled envelope (e.g. num_classes > 32) */
+  HALO_ERR_CUDA = -3,        /* a CUDA runtime call failed; message carries cudaGetErrorString */
+  HALO_ERR_WORKSPACE = -4    /* workspace pointer NULL or too small */
+} halo_status;
+
+/* what `feat` holds */
+typedef enum {
+  HALO_FEAT_TANGENT_F32 = 0, /* raw decoder features u (fp32): expmap0+project is fused in  (hyperbolic.py:28-39) */
+  HALO_FEAT_BALL_F32 = 1,    /* points already on the Poincare ball, fp32 */
+  HALO_FEAT_BALL_F64 = 2     /* points already on the ball, fp64 (what the reference hands HyperMLR) */
+} halo_feat_kind;
+
+/* per-pixel uncertainty written by the head / logits pass (floating_region.py:70-92,123-127) */
+typedef enum {
+  HALO_PIXUNC_ENTROPY = 0,   /* -sum p log(p+1e-6) / log(19)   (19 hard-coded, :74-76) */
+  HALO_PIXUNC_ONE_MINUS_PGT = 1 /* 1 - p[gt], gt==255 -> argmax   ("oracle_acc", :77-83) */
+} halo_pixunc_mode;
+
+typedef enum {
+  HALO_LABEL_ARGMAX = 0,     /* argmax_k p_k                    ("ripu", :166) */
+  HALO_LABEL_GT_FILLED = 1   /* gt with 255 replaced by argmax  ("oracle_ripu", :172-173) */
+} halo_label_mode;
+
+typedef enum {
+  HALO_NORM_RADIUS = 0,      /* Poincare distance to origin      (hyperbolic.py:74-83) */
+  HALO_NORM_EUCLID = 1       /* ||x||_2 of the ball point        ("euc_norm", floating_region.py:195) */
+} halo_norm_mode;
+
+/* region uncertainty (floating_region.py:70-92, 158-163) */
+typedef enum {
+  HALO_UNC_BOXSUM = 0,       /* k x k zero-padded box SUM of the per-pixel map ("entropy", "oracle_acc") */
+  HALO_UNC_PIXEL = 1,        /* the per-pixel map itself        ("pixel_entropy") */
+  HALO_UNC_ZERO = 2          /* zeros                            ("none" and every unknown string) */
+} halo_unc_mode;
+
+/* region impurity (floating_region.py:165-202) */
+typedef enum {
+  HALO_PUR_NORM = 0,         /* impurity := the radius / norm plane, count := 1   ("radius", "euc_norm") */
+  HALO_PUR_LABEL_HIST = 1,   /* k x k label-histogram entropy, count := window population ("ripu", "oracle_ripu") */
+  HALO_PUR_RADIUS_BINS = 2,  /* same over K quantised radius bins   ("hyper", :94-110; window is pk x pk) */
+  HALO_PUR_ZERO = 3          /* zeros, count := 1                    ("none") */
+} halo_pur_mode;
+
+int halo_abi_version(void);
+const char* halo_last_error(void);
+
+/* ---- Poincare-ball classifier head, forward -------------------------------------------------------
+ * Replaces HyperMapper.expmap (core/utils/hyperbolic.py:28-39), HyperMLR.forward/_hyper_logits
+ * (:120-188), HyperMapper.poincare_distance_origin (:74-83) and the softmax-entropy / argmax prologue of
+ * FloatingRegionScore.forward (core/active/floating_region.py:151-166) in ONE pass over the features.
+ *   feat   [N,C,H,W]  per `feat_kind`;  P, A [O,C] fp32 (HyperMLR.P_MLR / A_MLR);  c curvature > 0
+ * Optional outputs (NULL = skip):
+ *   logits [N,O,H,W] f32; radius [N,H,W] f32 (per norm_mode); pixunc [N,H,W] f32 (per pixunc_mode);
+ *   label [N,H,W] u8 (per label_mode); stats [N,4] f32 = {min,max of the radius plane, unused, unused}
+ *   gt [N,H,W] u8 is read only by HALO_PIXUNC_ONE_MINUS_PGT / HALO_LABEL_GT_FILLED.
+ * ws: halo_head_workspace_bytes(O, C) bytes of device scratch (packed class parameters). */
+size_t halo_head_workspace_bytes(int O, int C);
+int halo_head_fwd(const void* feat, int feat_kind, const float* P, const float* A, float c,
+                  float* logits, float* radius, float* pixunc, uint8_t* label, float* stats,
+                  const uint8_t* gt, int pixunc_mode, int label_mode, int norm_mode,
+                  int N, int C, int O, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
+
+/* ---- head backward (core/train_learners.py:238,362,457,557: autograd through expmap + HyperMLR) ----
+ *   feat [N,C,H,W] f32 raw features (HALO_FEAT_TANGENT_F32) ; dlogits [N,O,H,W] f32
+ *   dfeat [N,C,H,W] f32 ; dP, dA [O,C] f32 (overwritten, not accumulated) */
+size_t halo_head_bwd_workspace_bytes(int N, int C, int O, int H, int W);
+int halo_head_bwd(const float* feat, const float* P, const float* A, float c, const float* dlogits,
+                  float* dfeat, float* dP, float* dA, int N, int C, int O, int H, int W,
+                  void* ws, size_t ws_bytes, halo_stream_t stream);
+
+/* ---- eager pieces of the head (callers that need the materialised tensors) --------------------------
+ * halo_expmap0_project: HyperMapper.expmap (hyperbolic.py:28-39) on dim=1; out_f64 selects the output type. */
+int halo_expmap0_project(const float* u, void* x_out, int out_f64, float c, int N, int C, int H, int W,
+                         halo_stream_t stream);
+/* halo_ball_norm: poincare_distance_origin (:74-83) or ||x|| of points on the ball; stats as above (or NULL) */
+int halo_ball_norm(const void* x, int x_f64, float c, int norm_mode, float* out, float* stats,
+                   int N, int C, int H, int W, halo_stream_t stream);
+/* halo_logits_stats: softmax -> per-pixel uncertainty + label from explicit logits
+ * (floating_region.py:151-152, 70-83, 123-127, 166, 172-173). */
+int halo_logits_stats(const float* logits, const uint8_t* gt, int pixunc_mode, int label_mode,
+                      float* pixunc, uint8_t* label, int N, int O, int H, int W, halo_stream_t stream);
+
+/* ---- floating-region score (core/active/floating_region.py:129-217 after the softmax) ---------------
+ *   pixunc [N,H,W] f32, radius [N,H,W] f32 (+ its stats [N,4]), label [N,H,W] u8, active [N,H,W] u8|NULL
+ *   k = uncertainty window (odd), pk = purity window (odd; 3 when the module was built for "hyper"),
+ *   n_bins = class count for LABEL_HIST or K for RADIUS_BINS.
+ *   score [N,H,W] f32 (active!=0 -> -inf, build.py:146); impurity / uncertainty [N,H,W] f32 are
+ *   REQUIRED scratch+outputs (they receive the maps the reference returns). */
+size_t halo_score_workspace_bytes(int N);
+int halo_score(const float* pixunc, const float* radius, const float* radius_stats, const uint8_t* label,
+               const uint8_t* active, int unc_mode, int pur_mode, int normalize, int k, int pk, int n_bins,
+               float* score, float* impurity, float* uncertainty, int N, int H, int W,
+               void* ws, size_t ws_bytes, halo_stream_t stream);
+
+/* ---- budgeted greedy selection (core/active/build.py:27-64, select_pixels_to_label) -----------------
+ * Bit-exact equivalent of the sequential loop: repeat n_regions times { arg-max of score with ties to the
+ * smallest w then smallest h; stop at -inf; score/active window of radius mask_radius := -inf/1;
+ * selected window of radius active_radius := 1; active_mask window := gt window }.  In place on all four.
+ *   score [N,H,W] f32|f64; active, selected, active_mask, gt [N,H,W] u8
+ *   n_picked [N] i32 out; picks [N,n_regions] i32 out|NULL (h*W+w in pick order, -1 padded) */
+size_t halo_select_workspace_bytes(int N, int H, int W, int n_regions);
+int halo_select_f32(float* score, uint8_t* active, uint8_t* selected, uint8_t* active_mask, const uint8_t* gt,
+                    int n_regions, int active_radius, int mask_radius, int* n_picked, int* picks,
+                    int N, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
+int halo_select_f64(double* score, uint8_t* active, uint8_t* selected, uint8_t* active_mask, const uint8_t* gt,
+                    int n_regions, int active_radius, int mask_radius, int* n_picked, int* picks,
+                    int N, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HALO_B200_H */

@@ -1,0 +1,156 @@
+"""GPU: the fused head (halo_head_fwd / halo_head_bwd through the Python mirror of core/utils/hyperbolic.py)
+against the golden vectors frozen from the reference and against the fp64 oracle on seeded sweeps."""
+import pytest
+import torch
+
+import halo_b200
+from halo_b200 import synth
+from oracle import head as ohead
+from tests.util import TOL, rel_err, t
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_golden_logits_radius_fused(golden):
+    g = golden["head"]
+    for k in range(int(g["n_cases"])):
+        tag = "h%d_" % k
+        c = float(g[tag + "c"])
+        u = t(g[tag + "u"]).to(DEV)
+        res = halo_b200.head_forward(u, t(g[tag + "P"]).to(DEV), t(g[tag + "A"]).to(DEV), c, want_logits=True,
+                                     want_radius=True, want_stats=True)
+        assert rel_err(res["logits"], t(g[tag + "logits"])) <= TOL, k
+        assert rel_err(res["radius"], t(g[tag + "radius"])) <= TOL, k
+        ref_r = t(g[tag + "radius"]).float()
+        assert torch.allclose(res["stats"][:, 0].cpu(), ref_r.amin(dim=(1, 2)), rtol=1e-5)
+        assert torch.allclose(res["stats"][:, 1].cpu(), ref_r.amax(dim=(1, 2)), rtol=1e-5)
+
+
+def test_golden_logits_from_ball_points(golden):
+    """HyperMLR fed the reference's fp64 embedding (the reference call: conv_seg(decoder_out.double()))."""
+    g = golden["head"]
+    for k in range(int(g["n_cases"])):
+        tag = "h%d_" % k
+        c = float(g[tag + "c"])
+        x = t(g[tag + "x"]).to(DEV)
+        res = halo_b200.head_forward(x, t(g[tag + "P"]).to(DEV), t(g[tag + "A"]).to(DEV), c, kind="ball",
+                                     want_logits=True, want_radius=True)
+        assert rel_err(res["logits"], t(g[tag + "logits"])) <= TOL, k
+        assert rel_err(res["radius"], t(g[tag + "radius"])) <= TOL, k
+
+
+@pytest.mark.parametrize("c", [1.0, 0.5])
+@pytest.mark.parametrize("sigma", [0.01, 0.1, 0.3, 1.0])
+def test_sweep_vs_oracle_c256(c, sigma):
+    C, O, H, W = 256, 19, 24, 40
+    P, A = synth.head_params(O, C, seed=3, dtype=torch.float64)
+    u = torch.stack([synth.image_features(i, C, H, W, sigma=sigma) for i in range(2)])
+    logits, x, rad = ohead.head_forward(u, P, A, c)
+    res = halo_b200.head_forward(u.to(DEV), P.to(DEV), A.to(DEV), c, want_logits=True, want_radius=True,
+                                 want_pixunc=True, want_label=True)
+    assert rel_err(res["logits"], logits) <= TOL
+    assert rel_err(res["radius"], rad) <= TOL
+    p = torch.softmax(logits, dim=1)
+    ent = torch.sum(-p * torch.log(p + 1e-6), dim=1) / torch.log(torch.tensor(19.0))
+    assert rel_err(res["pixunc"], ent) <= TOL
+    agree = (res["label"].cpu().long() == p.argmax(dim=1)).float().mean().item()
+    assert agree >= 0.999
+
+
+@pytest.mark.parametrize("shape", [(16, 64, 9, 17), (19, 62, 7, 11), (3, 30, 5, 5), (32, 128, 8, 16), (21, 100, 6, 9)])
+def test_odd_shapes_and_class_counts(shape):
+    O, C, H, W = shape
+    P, A = synth.head_params(O, C, seed=5, dtype=torch.float64)
+    u = torch.stack([synth.image_features(i, C, H, W, sigma=0.25) for i in range(3)])
+    logits, x, rad = ohead.head_forward(u, P, A, 1.0)
+    res = halo_b200.head_forward(u.to(DEV), P.to(DEV), A.to(DEV), 1.0, want_logits=True, want_radius=True)
+    assert rel_err(res["logits"], logits) <= TOL
+    assert rel_err(res["radius"], rad) <= TOL
+
+
+def test_points_outside_and_zero_features():
+    C, O, H, W = 64, 19, 8, 8
+    P, A = synth.head_params(O, C, seed=7, dtype=torch.float64)
+    P[2] *= 9.0  # |p| > 1/sqrt(c): B_k < 0 branch
+    u = torch.randn(1, C, H, W) * 0.3
+    u[0, :, 0, 0] = 0.0  # a pixel at the origin
+    u[0, :, 1, 1] *= 100.0  # far outside: clipped by project
+    logits, x, rad = ohead.head_forward(u, P, A, 1.0)
+    res = halo_b200.head_forward(u.to(DEV), P.to(DEV), A.to(DEV), 1.0, want_logits=True, want_radius=True)
+    assert rel_err(res["logits"], logits) <= TOL
+    assert rel_err(res["radius"], rad) <= TOL
+
+
+def test_module_dropin_surface(golden):
+    g = golden["head"]
+    tag = "h1_"
+    c = float(g[tag + "c"])
+    u = t(g[tag + "u"]).to(DEV)
+    mapper = halo_b200.HyperMapper(c=c)
+    mlr = halo_b200.HyperMLR(u.shape[1], 19, c=c).to(DEV)
+    mlr.load_state_dict({"P_MLR": t(g[tag + "P"]), "A_MLR": t(g[tag + "A"])})
+    with torch.no_grad():
+        emb = mapper.expmap(u, dim=1)                    # classifier.py:553
+        out = mlr(emb.double()).float()                  # classifier.py:554
+    assert isinstance(emb, halo_b200.PoincareEmbedding)
+    assert rel_err(out, t(g[tag + "logits"])) <= TOL
+    assert rel_err(mapper.poincare_distance_origin(emb, dim=1), t(g[tag + "radius"])) <= TOL
+    x = emb.materialize()
+    assert x.dtype == torch.float64 and rel_err(x, t(g[tag + "x"])) <= 1e-6
+    # the handle behaves like a tensor for torch functions (build.py:133 F.interpolate(decoder_out, ...))
+    up = torch.nn.functional.interpolate(emb, size=(24, 40), mode="bilinear", align_corners=True)
+    ref_up = torch.nn.functional.interpolate(t(g[tag + "x"]), size=(24, 40), mode="bilinear", align_corners=True)
+    assert rel_err(up, ref_up) <= 1e-6
+    assert emb[0:1].shape[0] == 1 and isinstance(emb[0:1], halo_b200.PoincareEmbedding)
+    # eager paths on other layouts
+    v = torch.randn(5, 7, 33, device=DEV)
+    xe = mapper.expmap(v, dim=-1)
+    assert rel_err(xe, ohead.expmap(v.cpu(), c, dim=-1)) <= 1e-6
+    assert rel_err(mapper.poincare_distance_origin(xe, dim=-1), ohead.radius(ohead.expmap(v.cpu(), c, dim=-1), c, dim=-1)) <= TOL
+
+
+def test_backward_matches_golden(golden):
+    g = golden["head"]
+    for k in range(8):
+        tag = "h%d_" % k
+        c = float(g[tag + "c"])
+        du, dP, dA = halo_b200.head_backward(t(g[tag + "u"]).to(DEV), t(g[tag + "P"]).to(DEV), t(g[tag + "A"]).to(DEV),
+                                             c, t(g[tag + "dlogits"]).to(DEV))
+        # tolerance: 1e-4 of the largest gradient entry (fp32 recompute + analytic derivative vs fp64 autograd)
+        assert rel_err(du, t(g[tag + "du"])) <= 1e-4, (k, "du")
+        assert rel_err(dP, t(g[tag + "dP"])) <= 1e-4, (k, "dP")
+        assert rel_err(dA, t(g[tag + "dA"])) <= 1e-4, (k, "dA")
+
+
+def test_autograd_through_modules():
+    C, O, H, W = 64, 19, 12, 16
+    c = 1.0
+    P, A = synth.head_params(O, C, seed=11, dtype=torch.float64)
+    u = torch.randn(2, C, H, W) * 0.1
+    target = torch.randint(0, O, (2, H, W))
+    # oracle: CE loss through the fp64 head
+    u0 = u.clone().requires_grad_(True)
+    P0, A0 = P.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    lo = ohead.mlr_logits(ohead.expmap(u0, c, dim=1), P0, A0, c).float()
+    torch.nn.functional.cross_entropy(lo, target).backward()
+    mapper = halo_b200.HyperMapper(c=c)
+    mlr = halo_b200.HyperMLR(C, O, c=c).to(DEV)
+    mlr.load_state_dict({"P_MLR": P, "A_MLR": A})
+    u1 = u.to(DEV).requires_grad_(True)
+    out = mlr(mapper.expmap(u1, dim=1).double()).float()
+    torch.nn.functional.cross_entropy(out, target.to(DEV)).backward()
+    assert rel_err(u1.grad, u0.grad) <= 1e-4
+    assert rel_err(mlr.P_MLR.grad, P0.grad) <= 1e-4
+    assert rel_err(mlr.A_MLR.grad, A0.grad) <= 1e-4
+
+
+def test_backward_is_deterministic():
+    C, O, H, W = 32, 19, 40, 64
+    P, A = synth.head_params(O, C, seed=1)
+    u = (torch.randn(2, C, H, W) * 0.2).to(DEV)
+    dl = (torch.randn(2, O, H, W) * 1e-3).to(DEV)
+    a = halo_b200.head_backward(u, P.to(DEV), A.to(DEV), 1.0, dl)
+    b = halo_b200.head_backward(u, P.to(DEV), A.to(DEV), 1.0, dl)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)

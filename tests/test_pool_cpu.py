@@ -1,0 +1,108 @@
+"""CPU: host-side logic of the sharded acquisition round -- shard arithmetic, region budget, module surface,
+drop-in installation, and the world_size-2 all-gather over gloo."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import halo_b200
+from halo_b200 import pool
+from oracle import acquire as oacquire
+
+
+def test_shard_range_partitions_the_pool():
+    for n in (0, 1, 7, 8, 2975):
+        for world in (1, 2, 4, 8):
+            spans = [pool.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for a, b in zip(spans, spans[1:]):
+                assert a[1] == b[0]
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    assert pool.shard_range(2975, 7, 8) == (2604, 2975)
+
+
+def test_region_budget_matches_reference_formula():
+    for h, w, budget, rounds, rk in ((640, 1280, 0.05, 1, 1), (640, 1280, 0.05, 5, 1), (320, 640, 0.022, 1, 1),
+                                     (640, 1280, 0.022, 1, 2), (640, 1280, 0.022, 1, 0), (1024, 2048, 0.05, 5, 1)):
+        cfg = pool.AcquisitionConfig(radius_k=rk, budget=budget, n_rounds=rounds)
+        assert cfg.regions_per_image(h, w) == oacquire.region_budget(h, w, budget, rounds, rk)
+    assert pool.AcquisitionConfig(budget=0.05).regions_per_image(640, 1280) == 4552
+    assert pool.AcquisitionConfig(budget=0.05, n_rounds=5).regions_per_image(640, 1280) == 911
+
+
+def test_module_surface_matches_reference():
+    m = halo_b200.HyperMLR(64, 19, c=1.0)
+    assert set(m.state_dict()) == {"P_MLR", "A_MLR"}
+    assert tuple(m.P_MLR.shape) == (19, 64) and m.num_classes == 19 and float(m.K) == 1.0
+    # an fp64 checkpoint written by the reference loads (dtype-converting copy)
+    sd = {"P_MLR": torch.randn(19, 64, dtype=torch.float64), "A_MLR": torch.randn(19, 64, dtype=torch.float64)}
+    m.load_state_dict(sd)
+    assert torch.allclose(m.P_MLR.double(), sd["P_MLR"], atol=1e-6)
+    mapper = halo_b200.HyperMapper(c=0.5)
+    assert mapper.c == 0.5 and float(mapper.K) == -0.5
+    frs = halo_b200.FloatingRegionScore(in_channels=19, size=3, purity_type="hyper", K=100, curvature=1.0)
+    assert frs.purity_size == 3 and frs.K == 100
+    frs5 = halo_b200.FloatingRegionScore(in_channels=19, size=5, purity_type="hyper", K=50, curvature=1.0)
+    assert frs5.size == 5 and frs5.purity_size == 3  # floating_region.py:54-55
+    with pytest.raises(AssertionError):
+        halo_b200.FloatingRegionScore(size=4, purity_type="radius", curvature=1.0)
+
+
+def test_dropin_install_registers_reference_module_paths():
+    saved = {k: v for k, v in sys.modules.items() if k == "core" or k.startswith("core.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        patched = halo_b200.install()
+        assert "core.utils.hyperbolic" in patched
+        from core.utils.hyperbolic import HyperMapper, HyperMLR  # noqa
+        from core.active.build import RegionSelection, select_pixels_to_label  # noqa
+        from core.active.floating_region import FloatingRegionScore  # noqa
+
+        assert HyperMLR is halo_b200.HyperMLR and RegionSelection is halo_b200.RegionSelection
+    finally:
+        for k in [k for k in sys.modules if k == "core" or k.startswith("core.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gather_worker(rank, world, port, n_images, tmp):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = pool.shard_range(n_images, rank, world)
+        H, W = 6, 10
+        cnt = torch.arange(lo, hi, dtype=torch.int32) * 3 + 1
+        msk = torch.stack([torch.full((H, W), i % 251, dtype=torch.uint8) for i in range(lo, hi)]) if hi > lo else None
+        out = pool.gather_round(cnt if hi > lo else None, msk, n_images)
+        torch.save({"n_picked": out["n_picked"], "active_mask": out["active_mask"]}, os.path.join(tmp, "r%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [5, 1])
+def test_gather_round_world2_gloo(tmp_path, n_images):
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), n_images, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(str(tmp_path), "r%d.pt" % r)) for r in range(world)]
+    for o in outs:
+        assert o["n_picked"].tolist() == [3 * i + 1 for i in range(n_images)]
+        assert o["active_mask"].shape == (n_images, 6, 10)
+        for i in range(n_images):
+            assert int(o["active_mask"][i, 0, 0]) == i % 251
+    assert torch.equal(outs[0]["active_mask"], outs[1]["active_mask"])
