@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- acquisition throughput of the HALO hyperbolic hot path on B200 (Mpixel/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+A "step" is one pass of the hot path (fused head K1 -> region score K2 -> budgeted selection K3, plus the
+all-gather of counts/masks when N>1) over one batch of synthetic Cityscapes-shaped images that is resident in
+HBM: BASELINE.json configs[1] (1280x640 px, 256-d features, 19 classes, 3x3 regions, mask radius 5, 5 % budget,
+entropy x radius score, normalised).  The full 2 975-image pool (2.5 TB of features) is streamed through HBM in
+such batches; `value` is the steady-state rate of that stream.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(name="cfg2_gtav_cityscapes", pool_images=2975, H=640, W=1280, C=256, O=19, radius_k=1,
+                mask_radius_k=5, budget=0.05, n_rounds=1, uncertainty="entropy", purity="radius", normalize=True,
+                curvature=1.0, sigma=0.1)
+KERNELS_PER_STEP = 6  # head_pack, head_fwd, score_init, score_pass_a, score_pass_b, select
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_cfg():
+    import halo_b200
+
+    w = WORKLOAD
+    return halo_b200.AcquisitionConfig(num_classes=w["O"], curvature=w["curvature"], radius_k=w["radius_k"],
+                                       mask_radius_k=w["mask_radius_k"], budget=w["budget"], n_rounds=w["n_rounds"],
+                                       uncertainty=w["uncertainty"], purity=w["purity"], normalize=w["normalize"])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_sample(index, rows):
+    """Synthetic inputs of one bounded sample: the first `rows` rows of pool image `index`."""
+    from halo_b200 import synth
+
+    w = WORKLOAD
+    feat = synth.image_features(index, w["C"], w["H"], w["W"], sigma=w["sigma"])[:, :rows].unsqueeze(0).contiguous()
+    gt = synth.image_labels(index, w["O"], w["H"], w["W"])[:rows].long()
+    return feat, gt
+
+
+def cpu_reference_step(sample, P, A):
+    """One sample through the reference algorithm (fp64 expmap + HyperMLR, FloatingRegionScore, sequential
+    arg-max select) -- oracle/acquire.py.  Returns pixels processed."""
+    from oracle import acquire as oacquire
+
+    w = WORKLOAD
+    feat, gt = sample
+    H, W = gt.shape
+    oacquire.acquire_image(feat, P, A, gt, torch.zeros((H, W), dtype=torch.bool), torch.zeros((H, W), dtype=torch.bool),
+                           torch.full((H, W), 255, dtype=torch.int64), c=w["curvature"], radius_k=w["radius_k"],
+                           mask_radius_k=w["mask_radius_k"], budget=w["budget"], n_rounds=w["n_rounds"],
+                           unc_type=w["uncertainty"], pur_type=w["purity"], normalize=w["normalize"], fast_select=False)
+    return H * W
+
+
+def cpu_baseline(max_seconds=25.0):
+    """Time the oracle port on a bounded sample (whole images of the bench workload) for ~10-30 s."""
+    from halo_b200 import synth
+
+    w = WORKLOAD
+    torch.set_num_threads(os.cpu_count() or 1)
+    P, A = synth.head_params(w["O"], w["C"], seed=0, dtype=torch.float64)
+    rows = w["H"]
+    strip = cpu_sample(0, 64)
+    t0 = time.perf_counter()
+    cpu_reference_step(strip, P, A)  # warm-up on a strip (thread pools, allocator)
+    warm = time.perf_counter() - t0
+    if warm * (w["H"] / 64) > max_seconds:  # slow host: shrink the sample to a strip of rows
+        rows = max(64, int(w["H"] * max_seconds / (warm * (w["H"] / 64))) // 32 * 32)
+    px, t, n = 0, 0.0, 0
+    while n < 4:
+        sample = cpu_sample(1 + n, rows)  # generation is not timed
+        t1 = time.perf_counter()
+        px += cpu_reference_step(sample, P, A)
+        t += time.perf_counter() - t1
+        n += 1
+        if t > max_seconds * 0.6:
+            break
+    return {"value": round(px / t / 1e6, 5), "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d image(s) x %dx%d px of the bench workload through oracle/acquire.py (fp64 head, box-filter "
+                      "score, sequential arg-max selection), %.1f s" % (n, rows, w["W"], t)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own algorithm for this path on the host cores (oracle port; the
+    reference is pure Python/PyTorch and cannot travel to the GPU box -- see DESIGN.md)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from halo_b200 import synth
+
+    w = WORKLOAD
+    torch.set_num_threads(os.cpu_count() or 1)
+    P, A = synth.head_params(w["O"], w["C"], seed=0, dtype=torch.float64)
+    rows = w["H"]
+    strip = cpu_sample(0, 64)
+    t0 = time.perf_counter()
+    cpu_reference_step(strip, P, A)
+    est_full = (time.perf_counter() - t0) * (w["H"] / 64)
+    budget_s = 240.0
+    total = args.steps + args.warmup
+    if est_full * total > budget_s:
+        rows = max(32, int(w["H"] * budget_s / (est_full * total)) // 32 * 32)
+    ring = [cpu_sample(i, rows) for i in range(2)]  # inputs are generated before the timed region
+    for i in range(args.warmup):
+        cpu_reference_step(ring[i % 2], P, A)
+    t1 = time.perf_counter()
+    px = 0
+    for i in range(args.steps):
+        px += cpu_reference_step(ring[i % 2], P, A)
+    dt = time.perf_counter() - t1
+    value = px / dt / 1e6
+    sample = "per step: first %d rows of one %dx%d image (%d px) through oracle/acquire.py" % (rows, w["H"], w["W"], rows * w["W"])
+    line = {
+        "impl": "reference", "metric": "acquisition_throughput", "value": round(value, 5), "unit": "Mpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / max(args.steps, 1) * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(None, sample),
+        "cpu_baseline": {"value": round(value, 5), "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": round(value, 5), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(batch, note=None):
+    w = WORKLOAD
+    cfg = {"workload": "GTAV->Cityscapes-shaped acquisition round (BASELINE.json configs[1]): %d x %dx%d px pool, "
+                       "%d-d features, %d classes, 3x3 regions, mask radius %d, %.0f %% budget single-shot (%d picks/img), "
+                       "entropy x radius, normalised" % (w["pool_images"], w["W"], w["H"], w["C"], w["O"], w["mask_radius_k"],
+                                                          w["budget"] * 100, 4552),
+           "image": [w["H"], w["W"]], "channels": w["C"], "classes": w["O"], "budget": w["budget"],
+           "l2_policy": "inputs larger than L2 (one batch of features >> 126 MB)"}
+    if batch is not None:
+        cfg["images_per_step_per_gpu"] = batch
+    if note:
+        cfg["sample"] = note
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+
+    import halo_b200
+    from halo_b200 import pool, synth
+    from halo_b200 import _native as nat
+
+    w = WORKLOAD
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+    nat.load()
+    cfg = make_cfg()
+    B, C, O, H, W = args.batch, w["C"], w["O"], w["H"], w["W"]
+    P, A = synth.head_params(O, C, seed=0, device=dev)
+    # resident batch of this rank's shard of the pool (weak scaling: B images per GPU per step)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    feat = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+    for i in range(B):
+        feat[i] = torch.randn((C, H, W), generator=g, device=dev, dtype=torch.float32) * w["sigma"]
+    gt = torch.randint(0, O, (B, H, W), generator=g, device=dev, dtype=torch.int64).to(torch.uint8)
+    gt[torch.rand((B, H, W), generator=g, device=dev) < 0.05] = 255
+    total_steps = args.steps + args.warmup
+    # fresh round-1 state per step, allocated up front so that no fill kernel runs inside the timed region
+    n_state = min(total_steps, 64)
+    state = [dict(active=torch.zeros((B, H, W), dtype=torch.uint8, device=dev),
+                  selected=torch.zeros((B, H, W), dtype=torch.uint8, device=dev),
+                  active_mask=torch.full((B, H, W), 255, dtype=torch.uint8, device=dev)) for _ in range(n_state)]
+
+    def reset(s):
+        s["active"].zero_(); s["selected"].zero_(); s["active_mask"].fill_(255)
+
+    def step(s):
+        res = halo_b200.acquire_batch(feat, P, A, cfg, gt, s["active"], s["selected"], s["active_mask"])
+        if distributed:
+            pool.gather_round(res["n_picked"], s["active_mask"], B * world)
+        return res
+
+    for i in range(args.warmup):
+        res = step(state[i % n_state])
+    torch.cuda.synchronize()
+    picks_ok = int(res["n_picked"].min().item()) if args.warmup else None
+    for s in state:
+        reset(s)
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    done = 0
+    while done < args.steps:
+        chunk = min(n_state, args.steps - done)
+        for j in range(chunk):
+            res = step(state[j])
+        done += chunk
+        if done < args.steps:  # recycle the state planes (outside the hot path; counted in the timed region)
+            for j in range(min(n_state, args.steps - done)):
+                reset(state[j])
+    ev1.record()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    clocks = sampler.finish()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    px_step = B * H * W * world
+    value = px_step * args.steps / (ms_total / 1e3) / 1e6
+
+    # ---- roofline of the dominant kernel (K1, fused head), timed alone on its launch stream ----
+    roof = None
+    e2e = None
+    cpu = None
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        reps = 5
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(2):
+            halo_b200.head_forward(feat, P, A, cfg.curvature, want_logits=False, want_radius=True, want_pixunc=True)
+        k0.record()
+        for _ in range(reps):
+            halo_b200.head_forward(feat, P, A, cfg.curvature, want_logits=False, want_radius=True, want_pixunc=True)
+        k1.record()
+        torch.cuda.synchronize()
+        k_ms = k0.elapsed_time(k1) / reps
+        alg_bytes = 4.0 * C * B * H * W  # features read once; SURVEY 8(d): radius/entropy planes are not algorithmic
+        achieved = alg_bytes / (k_ms / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": "head_fwd_kernel (K1 fused head)", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+                "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
+                "step_frac": round((4.0 * C + 13) * px_step / world * args.steps / (ms_total / 1e3) / 1e9 / peak, 4)}
+    if distributed:
+        dist.barrier()
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
+    e2e = run_e2e(args, cfg, P, A, dev, rank, world, distributed)
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        cpu = cpu_baseline()
+    if rank == 0:
+        line = {
+            "metric": "acquisition_throughput", "value": round(value, 2), "unit": "Mpixel/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(B), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": KERNELS_PER_STEP * args.steps, "picks_per_image": picks_ok,
+            "round_seconds_at_this_rate": round(w["pool_images"] * H * W / (value * 1e6), 4),
+        }
+        print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, cfg, P, A, dev, rank, world, distributed):
+    """Same metric through the public API from pinned HOST memory: per step the features, labels and mask state of
+    `e2e_batch` images are copied host->device, scored and selected, and counts + updated masks copied back."""
+    import torch.distributed as dist
+
+    import halo_b200
+
+    w = WORKLOAD
+    Be, C, O, H, W = args.e2e_batch, w["C"], w["O"], w["H"], w["W"]
+    g = torch.Generator().manual_seed(99 + rank)
+    h_feat = torch.empty((Be, C, H, W), dtype=torch.float32).pin_memory()
+    h_feat.normal_(0.0, w["sigma"], generator=g)
+    h_gt = torch.randint(0, O, (Be, H, W), generator=g, dtype=torch.int64).to(torch.uint8).pin_memory()
+    h_active = torch.zeros((Be, H, W), dtype=torch.uint8).pin_memory()
+    h_mask_in = torch.full((Be, H, W), 255, dtype=torch.uint8).pin_memory()
+    h_mask_out = torch.empty((Be, H, W), dtype=torch.uint8).pin_memory()
+    h_cnt = torch.empty((Be,), dtype=torch.int32).pin_memory()
+    # double-buffered device staging: copy image i+1 while image i is scored (copy stream + compute stream)
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [dict(feat=torch.empty((1, C, H, W), dtype=torch.float32, device=dev),
+                  gt=torch.empty((1, H, W), dtype=torch.uint8, device=dev),
+                  active=torch.empty((1, H, W), dtype=torch.uint8, device=dev),
+                  selected=torch.zeros((1, H, W), dtype=torch.uint8, device=dev),
+                  mask=torch.empty((1, H, W), dtype=torch.uint8, device=dev),
+                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+    d_cnt = torch.empty((Be,), dtype=torch.int32, device=dev)
+    compute = torch.cuda.current_stream(dev)
+
+    def one_step():
+        for s in slots:
+            s["free"].record(compute)
+        for i in range(Be):
+            s = slots[i % 2]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(s["free"])
+                s["feat"].copy_(h_feat[i:i + 1], non_blocking=True)
+                s["gt"].copy_(h_gt[i:i + 1], non_blocking=True)
+                s["active"].copy_(h_active[i:i + 1], non_blocking=True)
+                s["mask"].copy_(h_mask_in[i:i + 1], non_blocking=True)
+                s["ready"].record(copy_stream)
+            compute.wait_event(s["ready"])
+            s["selected"].zero_()
+            res = halo_b200.acquire_batch(s["feat"], P, A, cfg, s["gt"], s["active"], s["selected"], s["mask"])
+            d_cnt[i:i + 1].copy_(res["n_picked"])
+            h_mask_out[i:i + 1].copy_(s["mask"], non_blocking=True)
+            s["free"].record(compute)
+        h_cnt.copy_(d_cnt, non_blocking=True)
+
+    steps = max(2, min(args.steps, 5))
+    for _ in range(2):
+        one_step()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one_step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    assert int(h_cnt.min()) > 0
+    px = Be * H * W * world * steps
+    h2d = Be * (C * H * W * 4 + 3 * H * W)
+    d2h = Be * (H * W + 4)
+    return {"value": round(px / (float(ms.item()) / 1e3) / 1e6, 2), "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "images_per_step_per_gpu": Be, "steps": steps,
+            "note": "pinned host buffers -> PCIe H2D (double-buffered per image) -> K1/K2/K3 -> D2H of counts + masks"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images resident per GPU per step")
+    ap.add_argument("--e2e-batch", type=int, default=4, help="images per end-to-end step (pinned host memory)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
