@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhalo_sm100.so")
-SOURCES = ["abi.cu", "head_fwd.cu", "head_misc.cu", "head_bwd.cu", "score.cu", "select.cu"]
+SOURCES = ["abi.cu", "head_fwd.cu", "head_fwd_tc.cu", "head_misc.cu", "head_bwd.cu", "score.cu", "select.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
@@ -33,7 +33,7 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=None):
     """Compile every .cu to an object (in parallel) and link the shared library.  Returns the path."""
     if not force and not stale():
         return LIB
@@ -43,7 +43,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags or os.environ.get("HALO_EXTRA_NVCC", "").split()) + ["-c", src, "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs, logs = [], []
     for src, obj, p in procs:

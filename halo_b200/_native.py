@@ -17,6 +17,7 @@ _lib = None
 
 # enums of include/halo_b200.h
 FEAT_TANGENT_F32, FEAT_BALL_F32, FEAT_BALL_F64 = 0, 1, 2
+FEAT_FLAG_NO_TENSOR_CORE = 0x100
 PIXUNC_ENTROPY, PIXUNC_ONE_MINUS_PGT = 0, 1
 LABEL_ARGMAX, LABEL_GT_FILLED = 0, 1
 NORM_RADIUS, NORM_EUCLID = 0, 1

@@ -36,7 +36,7 @@ int sm_count();
 
 // ---- constants of the head that must be formed in double on the host ------------------------------
 struct HeadConsts {
-  float c, s, inv_s, two_over_s, two_s;
+  float c, inv_c, s, inv_s, two_over_s, two_s;
   float z_clip;      // artanh(1-1e-5): tanh(z) > 1-1e-5  <=>  z > z_clip   (geoopt project eps for fp64)
   float t_clip;      // 1-1e-5
   float omega_clip;  // 1-(1-1e-5)^2
@@ -50,6 +50,7 @@ inline HeadConsts make_head_consts(float c) {
   HeadConsts h;
   double cd = (double)c, s = sqrt(cd);
   h.c = c;
+  h.inv_c = (float)(1.0 / cd);
   h.s = (float)s;
   h.inv_s = (float)(1.0 / s);
   h.two_over_s = (float)(2.0 / s);

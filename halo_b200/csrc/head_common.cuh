@@ -63,4 +63,129 @@ static __global__ void head_pack_kernel(const float* __restrict__ P, const float
 }
 
 
+// ---- per-pixel epilogue (shared by every head kernel) ---------------------------------------------------
+struct PixelScalars {
+  float gamma;   // x = gamma * u
+  float t2;      // c*|x|^2
+  float omega;   // 1 - c*|x|^2
+  float radius;  // (2/s) artanh(s|x|)
+  float xnorm;   // |x|
+};
+
+// raw features: expmap0 + project fused (hyperbolic.py:37-38 with geoopt's fp64 eps 1e-5).  Once per pixel,
+// so the accurate libm versions are affordable.
+__device__ __forceinline__ PixelScalars tangent_scalars(float n2, const HeadConsts& hc) {
+  PixelScalars ps;
+  const float n = sqrtf(n2);
+  const float sn = hc.s * n;
+  const bool clipped = sn > hc.z_clip;  // tanh(min(sn,15)) > 1-1e-5
+  const float z = fminf(sn, hc.z_clip);
+  const float e = expf(-2.f * z);
+  const float t = clipped ? hc.t_clip : tanhf(z);
+  const float ope = 1.f + e;
+  ps.omega = clipped ? hc.omega_clip : 4.f * e / (ope * ope);  // sech^2(z): never form 1 - t^2
+  ps.gamma = t / (hc.s * fmaxf(n, 1e-15f));
+  ps.t2 = t * t;
+  ps.radius = hc.two_over_s * z;
+  ps.xnorm = t * hc.inv_s;
+  return ps;
+}
+
+// points already on the ball: |x|^2 arrives in double so that 1 - c|x|^2 keeps its leading digits
+__device__ __forceinline__ PixelScalars ball_scalars(double n2, const HeadConsts& hc) {
+  PixelScalars ps;
+  const double cx = (double)hc.c * n2;
+  ps.gamma = 1.f;
+  ps.t2 = (float)cx;
+  ps.omega = (float)(1.0 - cx);
+  const double t = fmin(sqrt(cx), 1.0 - 1e-7);  // geoopt artanh clamp
+  ps.radius = hc.two_over_s * (float)(0.5 * (log1p(t) - log1p(-t)));
+  ps.xnorm = (float)sqrt(n2);
+  return ps;
+}
+
+// asinh through the SFU: sign(x) * ln(|x| + sqrt(x^2+1)); absolute error ~2e-7, which the logit tolerance
+// (1e-5 of max|logit|) absorbs with a wide margin (DESIGN.md "K1 numerics").
+__device__ __forceinline__ float fast_asinh(float x) {
+  const float ax = fabsf(x);
+  const float r = (ax > 1e8f) ? (__logf(ax) + 0.69314718f) : __logf(ax + sqrtf(fmaf(ax, ax, 1.f)));
+  return copysignf(r, x);
+}
+
+// HyperMLR logit for one class from the two contractions (hyperbolic.py:146-183)
+__device__ __forceinline__ float mlr_logit(float S, float T, const PixelScalars& ps, float pp, float an, float pa,
+                                           float Bk, const HeadConsts& hc) {
+  const float px = ps.gamma * S;
+  const float xa = ps.gamma * T;
+  const float cpx2 = 2.f * hc.c * px;
+  const float Anum = 1.f + cpx2 + ps.t2;                                  // :150
+  const float D = fmaxf(fmaf(hc.c * ps.t2, pp, 1.f + cpx2), 1e-12f);      // :152-153
+  const float num = fmaf(Bk, xa, Anum * pa);                              // D * <(-p)(+)x, a_hat>   (:175-177)
+  const float bo = Bk * ps.omega;
+  const float invD = __fdividef(1.f, D);
+  const float omc = bo * invD;                                            // 1 - c*|(-p)(+)x|^2
+  float arg;
+  if (omc >= hc.om_max) {
+    arg = __fdividef(hc.two_s * num, fmaxf(bo, 1e-12f * D));              // inside the MLR ball: D cancels (:179-180)
+  } else {
+    const float m = fmaxf(1.f - omc, 0.f) * hc.inv_c;                     // |(-p)(+)x|^2
+    arg = num * invD * hc.out_scale * rsqrtf(fmaxf(m, 1e-24f));           // projected to maxnorm (:162-170)
+  }
+  return hc.two_over_s * an * fast_asinh(arg);                            // :181-183 (lambda_term = 2.0)
+}
+
+// softmax entropy (floating_region.py:72-76) / 1-p[gt] (:77-83) and arg-max (:166) from logits in registers
+template <int OP>
+__device__ __forceinline__ void softmax_stats(const float (&l)[OP], int O, const HeadConsts& hc, int pixunc_mode,
+                                              int label_mode, int gt, float& pixunc, int& label) {
+  float mx = l[0];
+  int arg = 0;
+#pragma unroll
+  for (int k = 1; k < OP; ++k)
+    if (k < O && l[k] > mx) { mx = l[k]; arg = k; }
+  float e[OP];
+  float Z = 0.f;
+#pragma unroll
+  for (int k = 0; k < OP; ++k) {
+    e[k] = (k < O) ? __expf(l[k] - mx) : 0.f;
+    Z += e[k];
+  }
+  const float iz = __fdividef(1.f, Z);
+  const int gtf = (gt == 255) ? arg : gt;
+  if (pixunc_mode == HALO_PIXUNC_ENTROPY) {
+    float ent = 0.f;
+#pragma unroll
+    for (int k = 0; k < OP; ++k) {
+      const float p = e[k] * iz;
+      if (k < O) ent -= p * __logf(p + 1e-6f);
+    }
+    pixunc = ent * hc.inv_log19;
+  } else {
+    float pg = 0.f;
+#pragma unroll
+    for (int k = 0; k < OP; ++k)
+      if (k == gtf) pg = e[k] * iz;
+    pixunc = 1.f - pg;
+  }
+  label = (label_mode == HALO_LABEL_GT_FILLED) ? gtf : arg;
+}
+
+// arguments shared by the CUDA-core and tensor-core forward kernels
+struct HeadArgs {
+  const void* feat;
+  const float* ws;
+  float* logits;
+  float* radius;
+  float* pixunc;
+  uint8_t* label;
+  float* stats;
+  const uint8_t* gt;
+  int pixunc_mode, label_mode, norm_mode;
+  int N, C, CPAD, O, HW;
+  int tiles_per_img, total_tiles;
+  int debug_raw, tc_variant;  // numerics probes (0 in production)
+  HeadConsts hc;
+};
+
+
 }  // namespace halo

@@ -7,133 +7,18 @@
 // core/active/floating_region.py:72-76,152,166 (entropy / argmax).  The closed form and its fp32-safe
 // rewrites (sech^2 for 1-c|x|^2, the (1-c|p|^2)(1-c|x|^2)/D identity for 1-c|(-p)(+)x|^2) are
 // derived in DESIGN.md section "K1".
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "head_common.cuh"
+#include "head_tc.cuh"
 
 namespace halo {
 
 constexpr int HEAD_THREADS = 256;
 constexpr int HEAD_PIX = 2;  // pixels per thread
 constexpr int HEAD_U = 4;    // channels per software-pipeline stage
-
-// ---- per-pixel epilogue ------------------------------------------------------------------------------
-struct PixelScalars {
-  float gamma;   // x = gamma * u
-  float t2;      // c*|x|^2
-  float omega;   // 1 - c*|x|^2
-  float radius;  // (2/s) artanh(s|x|)
-  float xnorm;   // |x|
-};
-
-// raw features: expmap0 + project fused (hyperbolic.py:37-38 with geoopt's fp64 eps 1e-5)
-__device__ __forceinline__ PixelScalars tangent_scalars(float n2, const HeadConsts& hc) {
-  PixelScalars ps;
-  const float n = sqrtf(n2);
-  const float sn = hc.s * n;
-  const bool clipped = sn > hc.z_clip;  // tanh(min(sn,15)) > 1-1e-5
-  const float z = fminf(sn, hc.z_clip);
-  const float e = expf(-2.f * z);
-  const float t = clipped ? hc.t_clip : tanhf(z);
-  const float ope = 1.f + e;
-  ps.omega = clipped ? hc.omega_clip : 4.f * e / (ope * ope);  // sech^2(z): never form 1 - t^2
-  ps.gamma = t / (hc.s * fmaxf(n, 1e-15f));
-  ps.t2 = t * t;
-  ps.radius = hc.two_over_s * z;
-  ps.xnorm = t * hc.inv_s;
-  return ps;
-}
-
-// points already on the ball: |x|^2 arrives in double so that 1 - c|x|^2 keeps its leading digits
-__device__ __forceinline__ PixelScalars ball_scalars(double n2, const HeadConsts& hc) {
-  PixelScalars ps;
-  const double cx = (double)hc.c * n2;
-  ps.gamma = 1.f;
-  ps.t2 = (float)cx;
-  ps.omega = (float)(1.0 - cx);
-  const double t = fmin(sqrt(cx), 1.0 - 1e-7);  // geoopt artanh clamp
-  ps.radius = hc.two_over_s * (float)(0.5 * (log1p(t) - log1p(-t)));
-  ps.xnorm = (float)sqrt(n2);
-  return ps;
-}
-
-// HyperMLR logit for one class from the two contractions (hyperbolic.py:146-183)
-__device__ __forceinline__ float mlr_logit(float S, float T, const PixelScalars& ps, float pp, float an, float pa,
-                                           float Bk, const HeadConsts& hc) {
-  const float px = ps.gamma * S;
-  const float xa = ps.gamma * T;
-  const float cpx2 = 2.f * hc.c * px;
-  const float Anum = 1.f + cpx2 + ps.t2;                              // :150
-  const float D = fmaxf(1.f + cpx2 + hc.c * ps.t2 * pp, 1e-12f);      // :152-153
-  const float num = Bk * xa + Anum * pa;                              // D * <(-p)(+)x, a_hat>   (:175-177)
-  const float bo = Bk * ps.omega;
-  const float omc = bo / D;                                           // 1 - c*|(-p)(+)x|^2
-  float arg;
-  if (omc >= hc.om_max) {
-    arg = hc.two_s * num / fmaxf(bo, 1e-12f * D);                     // inside the MLR ball: D cancels (:179-180)
-  } else {
-    const float m = fmaxf(1.f - omc, 0.f) * (1.f / hc.c);             // |(-p)(+)x|^2
-    const float root = fmaxf(sqrtf(m), 1e-12f);
-    arg = (num / D) * (hc.out_scale / root);                          // projected to maxnorm (:162-170)
-  }
-  return hc.two_over_s * an * asinhf(arg);                            // :181-183 (lambda_term = 2.0)
-}
-
-template <int OP, int PIX>
-struct SoftmaxOut {
-  float pixunc[PIX];
-  int label[PIX];
-};
-
-// softmax entropy (floating_region.py:72-76) / 1-p[gt] (:77-83) and arg-max (:166) from logits in registers
-template <int OP>
-__device__ __forceinline__ void softmax_stats(const float (&l)[OP], int O, const HeadConsts& hc, int pixunc_mode,
-                                              int label_mode, int gt, float& pixunc, int& label) {
-  float mx = l[0];
-  int arg = 0;
-#pragma unroll
-  for (int k = 1; k < OP; ++k)
-    if (k < O && l[k] > mx) { mx = l[k]; arg = k; }
-  float e[OP];
-  float Z = 0.f;
-#pragma unroll
-  for (int k = 0; k < OP; ++k) {
-    e[k] = (k < O) ? __expf(l[k] - mx) : 0.f;
-    Z += e[k];
-  }
-  const float iz = 1.f / Z;
-  const int gtf = (gt == 255) ? arg : gt;
-  if (pixunc_mode == HALO_PIXUNC_ENTROPY) {
-    float ent = 0.f;
-#pragma unroll
-    for (int k = 0; k < OP; ++k) {
-      const float p = e[k] * iz;
-      if (k < O) ent -= p * __logf(p + 1e-6f);
-    }
-    pixunc = ent * hc.inv_log19;
-  } else {
-    float pg = 0.f;
-#pragma unroll
-    for (int k = 0; k < OP; ++k)
-      if (k == gtf) pg = e[k] * iz;
-    pixunc = 1.f - pg;
-  }
-  label = (label_mode == HALO_LABEL_GT_FILLED) ? gtf : arg;
-}
-
-struct HeadArgs {
-  const void* feat;
-  const float* ws;
-  float* logits;
-  float* radius;
-  float* pixunc;
-  uint8_t* label;
-  float* stats;
-  const uint8_t* gt;
-  int pixunc_mode, label_mode, norm_mode;
-  int N, C, CPAD, O, HW;
-  int tiles_per_img, total_tiles;
-  HeadConsts hc;
-};
 
 template <int KIND>
 struct FeatLoad;
@@ -215,40 +100,42 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) head_fwd_kernel(const HeadArg
     }
 
     if (TANGENT) {
-      float cur[HEAD_U][HEAD_PIX], nxt[HEAD_U][HEAD_PIX];
-#pragma unroll
-      for (int j = 0; j < HEAD_U; ++j) {
-        if (j < a.C) load_pair<T, VEC>(base + (size_t)j * HW, p, HW, cur[j]);
-        else cur[j][0] = cur[j][1] = 0.f;
-      }
-      for (int cb = 0; cb < a.CPAD; cb += HEAD_U) {
+      // software pipeline, two register buffers used alternately (no buffer copies): while the FMAs of
+      // HEAD_U channels issue, the loads of the next HEAD_U channels are in flight
+      float bufA[HEAD_U][HEAD_PIX], bufB[HEAD_U][HEAD_PIX];
+      auto load_stage = [&](float (&dst)[HEAD_U][HEAD_PIX], int cb) {
 #pragma unroll
         for (int j = 0; j < HEAD_U; ++j) {
-          const int ch = cb + HEAD_U + j;
-          if (ch < a.C) load_pair<T, VEC>(base + (size_t)ch * HW, p, HW, nxt[j]);
-          else nxt[j][0] = nxt[j][1] = 0.f;
+          const int ch = cb + j;
+          if (ch < a.C) load_pair<T, VEC>(base + (size_t)ch * HW, p, HW, dst[j]);
+          else dst[j][0] = dst[j][1] = 0.f;
         }
+      };
+      auto fma_stage = [&](const float (&src)[HEAD_U][HEAD_PIX], int cb) {
 #pragma unroll
         for (int j = 0; j < HEAD_U; ++j) {
           const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)(cb + j) * KP);
 #pragma unroll
-          for (int i = 0; i < HEAD_PIX; ++i) n2[i] = fmaf(cur[j][i], cur[j][i], n2[i]);
+          for (int i = 0; i < HEAD_PIX; ++i) n2[i] = fmaf(src[j][i], src[j][i], n2[i]);
 #pragma unroll
           for (int q = 0; q < KP / 4; ++q) {
             const float4 w = w4[q];
 #pragma unroll
             for (int i = 0; i < HEAD_PIX; ++i) {
-              acc[i][4 * q + 0] = fmaf(cur[j][i], w.x, acc[i][4 * q + 0]);
-              acc[i][4 * q + 1] = fmaf(cur[j][i], w.y, acc[i][4 * q + 1]);
-              acc[i][4 * q + 2] = fmaf(cur[j][i], w.z, acc[i][4 * q + 2]);
-              acc[i][4 * q + 3] = fmaf(cur[j][i], w.w, acc[i][4 * q + 3]);
+              acc[i][4 * q + 0] = fmaf(src[j][i], w.x, acc[i][4 * q + 0]);
+              acc[i][4 * q + 1] = fmaf(src[j][i], w.y, acc[i][4 * q + 1]);
+              acc[i][4 * q + 2] = fmaf(src[j][i], w.z, acc[i][4 * q + 2]);
+              acc[i][4 * q + 3] = fmaf(src[j][i], w.w, acc[i][4 * q + 3]);
             }
           }
         }
-#pragma unroll
-        for (int j = 0; j < HEAD_U; ++j)
-#pragma unroll
-          for (int i = 0; i < HEAD_PIX; ++i) cur[j][i] = nxt[j][i];
+      };
+      load_stage(bufA, 0);
+      for (int cb = 0; cb < a.CPAD; cb += 2 * HEAD_U) {
+        load_stage(bufB, cb + HEAD_U);
+        fma_stage(bufA, cb);
+        load_stage(bufA, cb + 2 * HEAD_U);
+        if (cb + HEAD_U < a.CPAD) fma_stage(bufB, cb + HEAD_U);
       }
     } else {
       // compatibility path (points already on the ball): |x|^2 in double, one channel at a time
@@ -273,29 +160,47 @@ __global__ void __launch_bounds__(HEAD_THREADS, 2) head_fwd_kernel(const HeadArg
       }
     }
 
-    // ---- epilogue, all in registers ----
+    // ---- epilogue, all in registers.  The pixel loop is deliberately NOT unrolled: the per-pixel code
+    // (OP classes of Mobius algebra + softmax) is ~1.5k instructions and two copies thrash the instruction cache.
     float rmin = __int_as_float(0x7f800000), rmax = 0.f;
     float out_rad[HEAD_PIX], out_unc[HEAD_PIX];
     int out_lab[HEAD_PIX];
 #pragma unroll
+    for (int i = 0; i < HEAD_PIX; ++i) { out_rad[i] = 0.f; out_unc[i] = 0.f; out_lab[i] = 0; }
+#pragma unroll 1
     for (int i = 0; i < HEAD_PIX; ++i) {
-      const PixelScalars ps = TANGENT ? tangent_scalars(n2[i], hc) : ball_scalars(n2d[i], hc);
+      const bool second = (i != 0);
+      const PixelScalars ps = TANGENT ? tangent_scalars(second ? n2[1] : n2[0], hc)
+                                      : ball_scalars(second ? n2d[1] : n2d[0], hc);
       float l[OP];
 #pragma unroll
-      for (int k = 0; k < OP; ++k)
-        l[k] = mlr_logit(acc[i][k], acc[i][OP + k], ps, sCls[k], sCls[OP + k], sCls[2 * OP + k], sCls[3 * OP + k], hc);
+      for (int k = 0; k < OP; ++k) {
+        const float S = second ? acc[1][k] : acc[0][k];
+        const float T = second ? acc[1][OP + k] : acc[0][OP + k];
+        l[k] = mlr_logit(S, T, ps, sCls[k], sCls[OP + k], sCls[2 * OP + k], sCls[3 * OP + k], hc);
+      }
+#ifdef HALO_TC_VARIANTS
+      if (a.debug_raw) {
 #pragma unroll
-      for (int k = 0; k < OP; ++k) acc[i][k] = l[k];
+        for (int k = 0; k < OP; ++k) l[k] = second ? acc[1][OP + k] : acc[0][OP + k];
+      }
+#endif
+#pragma unroll
+      for (int k = 0; k < OP; ++k) {
+        if (second) acc[1][k] = l[k];
+        else acc[0][k] = l[k];
+      }
       const float r = (a.norm_mode == HALO_NORM_EUCLID) ? ps.xnorm : ps.radius;
-      out_rad[i] = r;
       if (p + i < HW) { rmin = fminf(rmin, r); rmax = fmaxf(rmax, r); }
-      out_unc[i] = 0.f;
-      out_lab[i] = 0;
+      float unc = 0.f;
+      int lab = 0;
       if (a.pixunc != nullptr || a.label != nullptr) {
         int g = 255;
         if (a.gt != nullptr && p + i < HW) g = a.gt[(size_t)n * HW + p + i];
-        softmax_stats<OP>(l, a.O, hc, a.pixunc_mode, a.label_mode, g, out_unc[i], out_lab[i]);
+        softmax_stats<OP>(l, a.O, hc, a.pixunc_mode, a.label_mode, g, unc, lab);
       }
+      if (second) { out_rad[1] = r; out_unc[1] = unc; out_lab[1] = lab; }
+      else { out_rad[0] = r; out_unc[0] = unc; out_lab[0] = lab; }
     }
 
     const size_t pix0 = (size_t)n * HW + p;
@@ -370,7 +275,9 @@ using namespace halo;
 extern "C" size_t halo_head_workspace_bytes(int O, int C) {
   if (O <= 0 || C <= 0) return 0;
   const int OP = head_op_pad(O), CPAD = round_up(C, HEAD_U);
-  return ((size_t)CPAD * 2 * OP + 4 * OP) * sizeof(float);
+  size_t std_bytes = ((size_t)CPAD * 2 * OP + 4 * OP) * sizeof(float);
+  std_bytes = (std_bytes + 255) / 256 * 256;
+  return std_bytes + head_tc_pack_floats(O, C) * sizeof(float);
 }
 
 extern "C" int halo_head_fwd(const void* feat, int feat_kind, const float* P, const float* A, float c, float* logits,
@@ -380,6 +287,8 @@ extern "C" int halo_head_fwd(const void* feat, int feat_kind, const float* P, co
   HALO_CHECK_ARG(feat && P && A, "halo_head_fwd: feat/P/A must not be NULL");
   HALO_CHECK_ARG(N > 0 && C > 0 && O > 0 && H > 0 && W > 0, "halo_head_fwd: non-positive dims N=%d C=%d O=%d H=%d W=%d", N, C, O, H, W);
   HALO_CHECK_ARG(c > 0.f, "halo_head_fwd: curvature c must be > 0 (got %g)", (double)c);
+  const bool no_tc = (feat_kind & HALO_FEAT_FLAG_NO_TENSOR_CORE) != 0;
+  feat_kind &= 0xff;
   HALO_CHECK_ARG(feat_kind >= 0 && feat_kind <= 2, "halo_head_fwd: bad feat_kind %d", feat_kind);
   HALO_CHECK_ARG(pixunc_mode >= 0 && pixunc_mode <= 1 && label_mode >= 0 && label_mode <= 1 && norm_mode >= 0 && norm_mode <= 1,
                  "halo_head_fwd: bad mode");
@@ -396,8 +305,9 @@ extern "C" int halo_head_fwd(const void* feat, int feat_kind, const float* P, co
     return HALO_ERR_WORKSPACE;
   }
   const int OP = head_op_pad(O), CPAD = round_up(C, HEAD_U);
-  const size_t smem = need;
-  if (smem > 200 * 1024) {
+  const size_t smem = ((size_t)CPAD * 2 * OP + 4 * OP) * sizeof(float);
+  const bool use_tc = !no_tc && head_tc_supported(feat_kind, C, O, H, W, feat);
+  if (!use_tc && smem > 200 * 1024) {
     set_error("halo_head_fwd: C=%d x O=%d class parameters (%zu B) exceed the shared-memory tile", C, O, smem);
     return HALO_ERR_UNSUPPORTED;
   }
@@ -413,6 +323,18 @@ extern "C" int halo_head_fwd(const void* feat, int feat_kind, const float* P, co
   a.tiles_per_img = (a.HW + HEAD_THREADS * HEAD_PIX - 1) / (HEAD_THREADS * HEAD_PIX);
   a.total_tiles = a.tiles_per_img * N;
   a.hc = make_head_consts(c);
+  a.debug_raw = 0;
+  a.tc_variant = 0;
+#ifdef HALO_TC_VARIANTS
+  if (const char* e = getenv("HALO_TC_DEBUG")) {  // numerics probe builds only: "<variant>[r]"
+    a.tc_variant = atoi(e);
+    a.debug_raw = strchr(e, 'r') != nullptr;
+  }
+#endif
+  if (use_tc) {
+    float* wtc = (float*)((unsigned char*)ws + (smem + 255) / 256 * 256);
+    return head_fwd_tc_launch(a, (const float*)ws, wtc, st);
+  }
   const size_t esz = (feat_kind == HALO_FEAT_BALL_F64) ? 8 : 4;
   bool vec = (a.HW % 2 == 0) && (((uintptr_t)feat) % (2 * esz) == 0);
   if (logits && ((uintptr_t)logits % 8)) vec = false;

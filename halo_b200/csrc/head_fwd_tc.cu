@@ -1,0 +1,510 @@
+// K1-TC -- fused Poincare-ball head, forward, Blackwell tensor-core path (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Why: the contraction [pixels x C] . [C x 2O] costs 2*C*(2O+1) ~ 20 kFLOP per 1 KB of features; the fp32 FMA
+// pipe tops out at ~40-59 % of the HBM roofline (profiles/r1_k1_cuda_core.md), so the contraction moves to the
+// 5th-gen tensor cores.  Plain TF32 (10-bit mantissa) would break the 1e-5 parity bound, so each operand is
+// split u = hi + lo (both TF32-representable, round-to-nearest) and three MMAs accumulate in fp32:
+//        D += U_hi.W_hi + U_lo.W_hi + U_hi.W_lo            (the dropped lo.lo term is ~2^-22 relative)
+//
+// Pipeline of one persistent CTA (one per SM, 384 threads):
+//   warps 0, 2        TMA producers (1 lane each, one per pixel warpgroup): [32 channels x 128 pixels] fp32 boxes of
+//                     the NCHW feature tensor (viewed as a 2-D [N*C, H*W] tensor) into that warpgroup's 3-deep
+//                     shared-memory ring (16 KB per stage), completion by mbarrier tx-count.
+//   warps 4-7, 8-11   two "pixel" warpgroups working on alternate 128-pixel tiles; thread = pixel = TMEM lane:
+//                       * convert: read the pixel's 32 channel values of a stage (conflict-free, pixels contiguous),
+//                         accumulate |u|^2, split hi/lo, tcgen05.st both into the A-operand columns of TMEM;
+//                       * epilogue: tcgen05.ld the 2*OP accumulator columns of the pixel and run the same
+//                         register epilogue as the CUDA-core kernel (Mobius algebra, asinh, radius, softmax entropy).
+//   warp 1 (1 lane)   MMA issuer: tcgen05.mma.kind::tf32, M=128 (pixels) x N=NP (2*OP padded to 16) x K=8,
+//                     A from TMEM, B (class parameters, hi and lo planes) from shared memory, D in TMEM;
+//                     tcgen05.commit releases A buffers / publishes accumulators through mbarriers.
+// The class parameters (<= 96 KB) stay resident in shared memory for the life of the CTA.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "head_common.cuh"
+#include "head_tc.cuh"
+
+namespace halo {
+
+constexpr int TC_BM = 128;      // pixels per tile = MMA M = TMEM lanes
+constexpr int TC_BK = 32;       // channels per pipeline stage
+constexpr int TC_WG_STAGES = 3;  // shared-memory stages per pixel warpgroup (each warpgroup has its own ring + producer)
+constexpr int TC_STAGES = TC_WG_STAGES * 2;
+constexpr int TC_STAGE_FLOATS = TC_BK * TC_BM;
+constexpr int TC_NWG = 2;       // pixel warpgroups
+constexpr int TC_THREADS = 128 + 128 * TC_NWG;
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_HK = 16;       // channels per A-operand half-buffer (two per pipeline stage)
+constexpr int TC_ACOLS = 2 * TC_HK;                 // per A half-buffer: 16 hi + 16 lo columns
+constexpr int TC_ACC_COL0 = TC_NWG * 2 * TC_ACOLS;  // = 128: accumulators start after the A buffers
+constexpr int TC_NACC_MAX = 4;  // partial accumulators per tile (shortens the in-TMEM accumulation chains)
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]     kind::tf32, cta_group::1
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cvt_rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(
+          taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, no swizzle ("interleaved" canonical layout, see head_tc.cuh)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version 1 (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+
+struct TcSmemLayout {
+  size_t w_bytes, ring_off, bar_off, tmem_off, cls_off, total;
+};
+__host__ __device__ inline TcSmemLayout tc_smem_layout(int NP, int OP, int C) {
+  TcSmemLayout L;
+  L.w_bytes = (size_t)2 * NP * C * 4;
+  L.ring_off = (L.w_bytes + 1023) / 1024 * 1024;
+  L.bar_off = L.ring_off + (size_t)TC_STAGES * TC_STAGE_FLOATS * 4;
+  const int nbars = 2 * TC_STAGES + TC_NWG * 2 * 2 + TC_NWG * 2;
+  L.tmem_off = L.bar_off + (size_t)nbars * 8;
+  L.cls_off = (L.tmem_off + 16 + 15) / 16 * 16;
+  L.total = L.cls_off + (size_t)4 * OP * 4;
+  return L;
+}
+
+// Accumulator plan (measured on B200, tools/tc_numerics.py, profiles/r1_tc_numerics.md): every tcgen05.mma rounds
+// its fp32 accumulator toward zero, a systematic ~2^-25.5 relative shrink per instruction, so the error of a dot
+// product grows LINEARLY with the number of MMAs chained on one accumulator.  Therefore
+//   * the dominant hi.hi products go to NMAIN "main" accumulators used round-robin by pipeline stage
+//     (C=256: 8 stages x 4 MMAs over 3 accumulators -> chains of <= 12 MMAs instead of 96), and
+//   * the two cross terms lo.hi + hi.lo (2^-11 of the main term, so their rounding is harmless) share one
+//     "correction" accumulator;
+// the epilogue adds the NMAIN+1 partial results in fp32 registers.
+template <int NP, int OP, int NMAIN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, const float* __restrict__ wtc) {
+  constexpr int NACC = NMAIN + 1;  // accumulator NMAIN is the correction accumulator
+  static_assert(TC_ACC_COL0 + TC_NWG * NACC * NP <= TC_TMEM_COLS, "TMEM column budget");
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int C = a.C;
+  const TcSmemLayout L = tc_smem_layout(NP, OP, C);
+  float* sW = reinterpret_cast<float*>(smem);  // [2][C/4][NP][4]: hi plane then lo plane
+  float* ring = reinterpret_cast<float*>(smem + L.ring_off);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TC_STAGES;
+  uint64_t* a_full = bars + 2 * TC_STAGES;               // [NWG][2]
+  uint64_t* a_empty = a_full + TC_NWG * 2;               // [NWG][2]
+  uint64_t* acc_full = a_empty + TC_NWG * 2;             // [NWG]
+  uint64_t* acc_empty = acc_full + TC_NWG;               // [NWG]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
+  float* sCls = reinterpret_cast<float*>(smem + L.cls_off);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup ----
+  {
+    const int n4 = 2 * NP * C / 4;
+    const float4* src = reinterpret_cast<const float4*>(wtc);
+    float4* dst = reinterpret_cast<float4*>(sW);
+    for (int i = threadIdx.x; i < n4; i += TC_THREADS) dst[i] = src[i];
+    const float* csrc = wtc + (size_t)2 * NP * C;
+    for (int i = threadIdx.x; i < 4 * OP; i += TC_THREADS) sCls[i] = csrc[i];
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 4);     // one elected lane per converter warp
+    }
+    for (int i = 0; i < TC_NWG * 2; ++i) {
+      mbar_init(&a_full[i], 4);
+      mbar_init(&a_empty[i], 1);   // tcgen05.commit
+    }
+    for (int g = 0; g < TC_NWG; ++g) {
+      mbar_init(&acc_full[g], 1);  // tcgen05.commit
+      mbar_init(&acc_empty[g], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy weight stores -> visible to the MMA (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int HW = a.HW;
+  const int cpt = C / TC_BK;  // chunks (pipeline stages) per tile
+  const int my_tiles = (blockIdx.x < a.total_tiles) ? (a.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (warp == 0 || warp == 2) {
+    // =================== TMA producers: warp 0 feeds warpgroup 0, warp 2 feeds warpgroup 1 ===================
+    // Each warpgroup owns a private ring (stages + barriers): a barrier then has exactly one producer and one
+    // consumer advancing in lock-step, which the 1-bit mbarrier phase parity requires.
+    const int g = warp >> 1;
+    if (lane == 0) {
+      for (int i = g; i < my_tiles; i += TC_NWG) {
+        const int it = i / TC_NWG;
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int n = tile / a.tiles_per_img;
+        const int p0 = (tile - n * a.tiles_per_img) * TC_BM;
+        for (int j = 0; j < cpt; ++j) {
+          const int q = it * cpt + j;                       // stage counter of this warpgroup
+          const int s = g * TC_WG_STAGES + q % TC_WG_STAGES;
+          const uint32_t ph = (uint32_t)(q / TC_WG_STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], TC_STAGE_FLOATS * 4);
+          tma_load_2d(ring + (size_t)s * TC_STAGE_FLOATS, &tmap, p0, n * C + j * TC_BK, &full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =================== MMA issuer ===================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N=NP, M=128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + (size_t)NP * C);
+      const uint32_t lbo = NP * 16, sbo = 128;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int g = i % TC_NWG, it = i / TC_NWG;
+        mbar_wait(&acc_empty[g], ((uint32_t)it & 1u) ^ 1u);
+        tc_fence_after();
+        for (int j = 0; j < cpt; ++j) {
+          const int ca = it * cpt + j;                      // stage counter of this warpgroup
+          const uint32_t d_main = tmem_base + TC_ACC_COL0 + (g * NACC + (j % NMAIN)) * NP;
+          const uint32_t d_corr = tmem_base + TC_ACC_COL0 + (g * NACC + NMAIN) * NP;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&a_full[g * 2 + h], (uint32_t)ca & 1u);
+            tc_fence_after();
+            const uint32_t a_col = tmem_base + (g * 2 + h) * TC_ACOLS;
+#pragma unroll
+            for (int ks = 0; ks < TC_HK / 8; ++ks) {
+              const uint32_t koff = (uint32_t)((j * TC_BK + h * TC_HK + ks * 8) / 4) * lbo;  // byte offset of the K-slice
+              const uint64_t b_hi = make_b_desc(w_hi + koff, lbo, sbo);
+              const uint64_t b_lo = make_b_desc(w_lo + koff, lbo, sbo);
+              const bool first_k = (h == 0 && ks == 0);
+              tc_mma_tf32_ts(d_main, a_col + ks * 8, b_hi, idesc, (j < NMAIN && first_k) ? 0u : 1u);   // hi . hi
+              tc_mma_tf32_ts(d_corr, a_col + TC_HK + ks * 8, b_hi, idesc, (j == 0 && first_k) ? 0u : 1u);  // lo . hi
+              tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);                                 // hi . lo
+            }
+            tc_commit(&a_empty[g * 2 + h]);
+          }
+        }
+        tc_commit(&acc_full[g]);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // =================== pixel warpgroups: convert + epilogue ===================
+    const int g = (warp - 4) >> 2;
+    const int wq = warp & 3;                   // TMEM lane quarter this warp may touch
+    const int m = wq * 32 + lane;              // pixel row inside the tile
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    const HeadConsts hc = a.hc;
+    for (int i = g; i < my_tiles; i += TC_NWG) {
+      const int it = i / TC_NWG;
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int n = tile / a.tiles_per_img;
+      const int p = (tile - n * a.tiles_per_img) * TC_BM + m;
+      float n2 = 0.f;
+      for (int j = 0; j < cpt; ++j) {
+        const int ca = it * cpt + j;                        // stage counter of this warpgroup
+        const int s = g * TC_WG_STAGES + ca % TC_WG_STAGES;
+        mbar_wait(&full[s], (uint32_t)(ca / TC_WG_STAGES) & 1u);
+        const float* src = ring + (size_t)s * TC_STAGE_FLOATS + m;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&a_empty[g * 2 + h], ((uint32_t)ca & 1u) ^ 1u);
+          tc_fence_after();
+          uint32_t hi[TC_HK], lo[TC_HK];
+#pragma unroll
+          for (int k = 0; k < TC_HK; ++k) {
+            const float u = src[(h * TC_HK + k) * TC_BM];
+            n2 = fmaf(u, u, n2);
+            const uint32_t hbits = cvt_rna_tf32(u);
+            hi[k] = hbits;
+            lo[k] = cvt_rna_tf32(u - __uint_as_float(hbits));
+          }
+          const uint32_t taddr = tmem_base + lane_addr + (g * 2 + h) * TC_ACOLS;
+          tmem_st_x16(taddr, hi);
+          tmem_st_x16(taddr + TC_HK, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[g * 2 + h]);
+        }
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+      // ---- epilogue: accumulators of this pixel ----
+      mbar_wait(&acc_full[g], (uint32_t)it & 1u);
+      tc_fence_after();
+      float S[OP], T[OP];
+#pragma unroll
+      for (int k = 0; k < OP; ++k) S[k] = T[k] = 0.f;
+      static_assert((2 * OP) % 8 == 0, "OP is a multiple of 4");
+#pragma unroll
+      for (int qa = 0; qa < NACC; ++qa) {
+        if (qa < cpt || qa == NMAIN) {  // main accumulators that received no stage (C < NMAIN*32) hold garbage
+          const uint32_t taddr = tmem_base + lane_addr + TC_ACC_COL0 + (g * NACC + qa) * NP;
+          float buf[8];
+#pragma unroll
+          for (int c8 = 0; c8 < (2 * OP) / 8; ++c8) {
+            tmem_ld_x8(taddr + c8 * 8, buf);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = c8 * 8 + e;
+              if (col < OP) S[col] += buf[e];
+              else T[col - OP] += buf[e];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[g]);
+
+      const bool live = (p < HW);
+      const PixelScalars ps = tangent_scalars(n2, hc);
+      float l[OP];
+#pragma unroll
+      for (int k = 0; k < OP; ++k)
+        l[k] = mlr_logit(S[k], T[k], ps, sCls[k], sCls[OP + k], sCls[2 * OP + k], sCls[3 * OP + k], hc);
+#ifdef HALO_TC_VARIANTS
+      if (a.debug_raw) {  // numerics probe: expose the raw contractions <u,a_hat_k> instead of the logits
+#pragma unroll
+        for (int k = 0; k < OP; ++k) l[k] = T[k];
+      }
+#endif
+      const float r = (a.norm_mode == HALO_NORM_EUCLID) ? ps.xnorm : ps.radius;
+      const size_t pix = (size_t)n * HW + p;
+      if (live) {
+        if (a.logits != nullptr) {
+#pragma unroll
+          for (int k = 0; k < OP; ++k)
+            if (k < a.O) __stcs(a.logits + ((size_t)n * a.O + k) * HW + p, l[k]);
+        }
+        if (a.radius != nullptr) __stcs(a.radius + pix, r);
+      }
+      if (a.pixunc != nullptr || a.label != nullptr) {
+        int gtv = 255;
+        if (a.gt != nullptr && live) gtv = a.gt[pix];
+        float unc;
+        int lab;
+        softmax_stats<OP>(l, a.O, hc, a.pixunc_mode, a.label_mode, gtv, unc, lab);
+        if (live) {
+          if (a.pixunc != nullptr) __stcs(a.pixunc + pix, unc);
+          if (a.label != nullptr) a.label[pix] = (uint8_t)lab;
+        }
+      }
+      if (a.stats != nullptr) {
+        const float rmin = warp_min(live ? r : __int_as_float(0x7f800000));
+        const float rmax = warp_max(live ? r : 0.f);
+        if (lane == 0) {
+          atomicMin(reinterpret_cast<int*>(a.stats + 4 * n + 0), __float_as_int(rmin));
+          atomicMax(reinterpret_cast<int*>(a.stats + 4 * n + 1), __float_as_int(rmax));
+        }
+      }
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ---- class parameters in the tensor-core operand layout ---------------------------------------------------
+// in : std pack  Wt[CPAD][2*OP] + cls[4][OP]     (head_pack_kernel)
+// out: W planes  [2 (hi,lo)][C/4][NP][4] fp32 with TF32-representable values (round-to-nearest split),
+//      followed by cls[4][OP].  Row n of the B operand: n < OP -> -P_n ; OP <= n < 2*OP -> a_hat_{n-OP} ; rest 0.
+__global__ void head_pack_tc_kernel(const float* __restrict__ std_pack, float* __restrict__ wtc, int C, int CPAD, int OP, int NP) {
+  const int KP = 2 * OP;
+  const int total = NP * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k4 = i / (NP * 4);
+    const int rem = i - k4 * NP * 4;
+    const int nrow = rem >> 2, kk = rem & 3;
+    const int ch = k4 * 4 + kk;
+    const float w = (nrow < KP) ? std_pack[(size_t)ch * KP + nrow] : 0.f;
+    uint32_t h, l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(w));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(w - __uint_as_float(h)));
+    wtc[i] = __uint_as_float(h);
+    wtc[(size_t)total + i] = __uint_as_float(l);
+  }
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < 4 * OP; i += blockDim.x) wtc[(size_t)2 * total + i] = std_pack[(size_t)CPAD * KP + i];
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int head_tc_np(int O) {
+  const int OP = head_op_pad(O);
+  return round_up(2 * OP, 16);
+}
+
+bool head_tc_supported(int feat_kind, int C, int O, int H, int W, const void* feat) {
+  if (feat_kind != HALO_FEAT_TANGENT_F32) return false;
+  if (C % TC_BK != 0 || C > 256 || C < TC_BK) return false;
+  if (O > 32) return false;
+  if (((long long)H * W) % 4 != 0) return false;          // TMA global stride must be a multiple of 16 bytes
+  if ((reinterpret_cast<uintptr_t>(feat) & 15) != 0) return false;
+  const TcSmemLayout L = tc_smem_layout(head_tc_np(O), head_op_pad(O), C);
+  if (L.total > 225 * 1024) return false;
+  return get_encode_fn() != nullptr;
+}
+
+size_t head_tc_pack_floats(int O, int C) { return (size_t)2 * head_tc_np(O) * C + 4 * head_op_pad(O); }
+
+template <int NP, int OP>
+static int launch_tc(const CUtensorMap& tmap, const HeadArgs& a, const float* wtc, size_t smem, int grid, cudaStream_t st) {
+  // as many main accumulators as TMEM allows next to the A buffers (at most one per pipeline stage of C=256)
+  constexpr int FIT = (TC_TMEM_COLS - TC_ACC_COL0) / (TC_NWG * NP) - 1;
+  constexpr int NMAIN = FIT > 8 ? 8 : FIT;
+  static_assert(NMAIN >= 2, "TMEM budget");
+  HALO_CUDA(cudaFuncSetAttribute(head_fwd_tc_kernel<NP, OP, NMAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  head_fwd_tc_kernel<NP, OP, NMAIN><<<grid, TC_THREADS, smem, st>>>(tmap, a, wtc);
+  return launch_status("head_fwd_tc_kernel");
+}
+
+int head_fwd_tc_launch(HeadArgs a, const float* std_pack, float* wtc, cudaStream_t st) {
+  const int OP = head_op_pad(a.O), NP = head_tc_np(a.O);
+  head_pack_tc_kernel<<<(NP * a.C + 255) / 256, 256, 0, st>>>(std_pack, wtc, a.C, a.CPAD, OP, NP);
+  int rc = launch_status("head_pack_tc_kernel");
+  if (rc) return rc;
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return HALO_ERR_CUDA;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)a.HW, (cuuint64_t)a.N * a.C};
+  const cuuint64_t gstride[1] = {(cuuint64_t)a.HW * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BM, (cuuint32_t)TC_BK};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(a.feat), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return HALO_ERR_CUDA;
+  }
+  a.tiles_per_img = (a.HW + TC_BM - 1) / TC_BM;
+  a.total_tiles = a.tiles_per_img * a.N;
+  const TcSmemLayout L = tc_smem_layout(NP, OP, a.C);
+  int grid = sm_count();
+  if (grid > a.total_tiles) grid = a.total_tiles;
+  switch (OP) {
+    case 4: return launch_tc<16, 4>(tmap, a, wtc, L.total, grid, st);
+    case 8: return launch_tc<16, 8>(tmap, a, wtc, L.total, grid, st);
+    case 12: return launch_tc<32, 12>(tmap, a, wtc, L.total, grid, st);
+    case 16: return launch_tc<32, 16>(tmap, a, wtc, L.total, grid, st);
+    case 20: return launch_tc<48, 20>(tmap, a, wtc, L.total, grid, st);
+    case 24: return launch_tc<48, 24>(tmap, a, wtc, L.total, grid, st);
+    case 28: return launch_tc<64, 28>(tmap, a, wtc, L.total, grid, st);
+    default: return launch_tc<64, 32>(tmap, a, wtc, L.total, grid, st);
+  }
+}
+
+}  // namespace halo

@@ -63,6 +63,38 @@ struct SelArgs {
   int n_regions, a_r, m_r, H, W, LB, cap, words;
 };
 
+// Visit every pixel of one image plane as f(p, value).  16-byte vector loads, 4 independent loads in flight per
+// thread (the scans are pure streaming passes; without the batching they are latency-bound at ~1 load/thread).
+template <typename S, typename F>
+__device__ __forceinline__ void scan_plane(const S* __restrict__ plane, int HW, int tid, F f) {
+  constexpr int V = 16 / (int)sizeof(S);
+  constexpr int UN = 4;
+  struct __align__(16) Vec { S e[V]; };
+  int done = 0;
+  if ((reinterpret_cast<uintptr_t>(plane) & 15) == 0) {
+    const int nvec = HW / V;
+    const Vec* vp = reinterpret_cast<const Vec*>(plane);
+    for (int base = tid; base < nvec; base += SEL_THREADS * UN) {
+      Vec v[UN];
+#pragma unroll
+      for (int j = 0; j < UN; ++j) {
+        const int idx = base + j * SEL_THREADS;
+        if (idx < nvec) v[j] = vp[idx];
+      }
+#pragma unroll
+      for (int j = 0; j < UN; ++j) {
+        const int idx = base + j * SEL_THREADS;
+        if (idx < nvec) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) f(idx * V + e, v[j].e[e]);
+        }
+      }
+    }
+    done = nvec * V;
+  }
+  for (int p = done + tid; p < HW; p += SEL_THREADS) f(p, plane[p]);
+}
+
 struct SelShared {
   unsigned hist[SEL_BINS];
   unsigned warp_tot[32];
@@ -115,16 +147,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const SelArgs<S>
       const unsigned dmask = (1u << nb) - 1u;
       for (int i = tid; i < SEL_BINS; i += SEL_THREADS) sh.hist[i] = 0u;
       __syncthreads();
-      for (int p = tid; p < HW; p += SEL_THREADS) {
-        const S v = score[p];
-        if (TR::dead(v)) continue;
-        if ((bitmap[p >> 5] >> (p & 31)) & 1u) continue;
+      scan_plane<S>(score, HW, tid, [&](int p, S v) {
+        if (TR::dead(v)) return;
+        if ((bitmap[p >> 5] >> (p & 31)) & 1u) return;
         const int h = p / W, w = p - h * W;
         const Comp ck = (TR::key(v) << LB) | (Comp)(LINMAX - (unsigned)(w * H + h));
-        if (ck > bound) continue;
-        if (level > 0 && (ck >> hi_bit) != prefix) continue;
+        if (ck > bound) return;
+        if (level > 0 && (ck >> hi_bit) != prefix) return;
         atomicAdd(&sh.hist[(unsigned)(ck >> shift) & dmask], 1u);
-      }
+      });
       __syncthreads();
       // suffix scan over bins (top bin first): thread t owns reversed indices 2t, 2t+1
       const int b_hi = SEL_BINS - 1 - 2 * tid, b_lo = b_hi - 1;
@@ -170,16 +201,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const SelArgs<S>
     // ---------------- 2. gather + sort (descending ckey) ----------------
     if (tid == 0) sh.cnt = 0u;
     __syncthreads();
-    for (int p = tid; p < HW; p += SEL_THREADS) {
-      const S v = score[p];
-      if (TR::dead(v)) continue;
-      if ((bitmap[p >> 5] >> (p & 31)) & 1u) continue;
+    scan_plane<S>(score, HW, tid, [&](int p, S v) {
+      if (TR::dead(v)) return;
+      if ((bitmap[p >> 5] >> (p & 31)) & 1u) return;
       const int h = p / W, w = p - h * W;
       const Comp ck = (TR::key(v) << LB) | (Comp)(LINMAX - (unsigned)(w * H + h));
-      if (ck > bound || ck < lo) continue;
+      if (ck > bound || ck < lo) return;
       const unsigned pos = atomicAdd(&sh.cnt, 1u);
       if (pos < (unsigned)a.cap) list[pos] = ck;
-    }
+    });
     __syncthreads();
     const int cnt = (int)min(sh.cnt, (unsigned)a.cap);
     int n2 = 32;

@@ -40,10 +40,12 @@ def _as_u8(t, name):
 
 def head_forward(feat, P, A, c=1.0, *, kind="tangent", want_logits=True, want_radius=False, want_pixunc=False,
                  want_label=False, want_stats=False, gt=None, pixunc_mode="entropy", label_mode="argmax",
-                 norm_mode="radius"):
+                 norm_mode="radius", tensor_cores=True):
     """One fused pass of the head over `feat` (N,C,H,W).  Returns a dict with the requested planes.
 
     kind: "tangent" (raw fp32 features, expmap fused) or "ball" (points already on the ball, fp32/fp64).
+    tensor_cores=False keeps the contraction on the fp32 CUDA cores (the tcgen05 3xTF32 path is the default
+    whenever the shape allows it: raw features, C % 32 == 0, C <= 256, H*W % 4 == 0).
     Wraps `halo_head_fwd` (include/halo_b200.h); replaces hyperbolic.py:28-39,74-83,120-188 and the
     softmax-entropy / argmax prologue of floating_region.py:151-166."""
     lib = nat.load()
@@ -52,7 +54,7 @@ def head_forward(feat, P, A, c=1.0, *, kind="tangent", want_logits=True, want_ra
         raise ValueError("head_forward: feat must be (N,C,H,W), got %s" % (tuple(feat.shape),))
     if kind == "tangent":
         feat = feat.contiguous() if feat.dtype == torch.float32 else feat.float().contiguous()
-        fk = nat.FEAT_TANGENT_F32
+        fk = nat.FEAT_TANGENT_F32 | (0 if tensor_cores else nat.FEAT_FLAG_NO_TENSOR_CORE)
     elif kind == "ball":
         if feat.dtype == torch.float64:
             fk = nat.FEAT_BALL_F64

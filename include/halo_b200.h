@@ -43,6 +43,8 @@ typedef enum {
   HALO_FEAT_BALL_F32 = 1,    /* points already on the Poincare ball, fp32 */
   HALO_FEAT_BALL_F64 = 2     /* points already on the ball, fp64 (what the reference hands HyperMLR) */
 } halo_feat_kind;
+/* OR-ed into feat_kind: keep the contraction on the fp32 CUDA cores (no tcgen05 path); used by parity tests */
+#define HALO_FEAT_FLAG_NO_TENSOR_CORE 0x100
 
 /* per-pixel uncertainty written by the head / logits pass (floating_region.py:70-92,123-127) */
 typedef enum {

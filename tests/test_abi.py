@@ -30,7 +30,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_workspace_queries_are_pure():
     lib = nat.load()
-    assert lib.halo_head_workspace_bytes(19, 256) == (256 * 40 + 80) * 4
+    std = (256 * 40 + 80) * 4  # CUDA-core pack: Wt[C][2*OP] + cls[4][OP]
+    tc = (2 * 48 * 256 + 80) * 4  # tensor-core pack: hi/lo planes [2][C/4][NP][4] + cls
+    assert lib.halo_head_workspace_bytes(19, 256) == (std + 255) // 256 * 256 + tc
     assert lib.halo_head_workspace_bytes(0, 256) == 0
     assert lib.halo_score_workspace_bytes(3) == 48
     assert lib.halo_select_workspace_bytes(2, 640, 1280, 4552) >= 2 * 4552 * 4 + 2 * 640 * 1280 // 8

@@ -40,15 +40,18 @@ def test_golden_logits_from_ball_points(golden):
         assert rel_err(res["radius"], t(g[tag + "radius"])) <= TOL, k
 
 
+@pytest.mark.parametrize("tensor_cores", [True, False], ids=["tcgen05", "cuda_core"])
 @pytest.mark.parametrize("c", [1.0, 0.5])
 @pytest.mark.parametrize("sigma", [0.01, 0.1, 0.3, 1.0])
-def test_sweep_vs_oracle_c256(c, sigma):
+def test_sweep_vs_oracle_c256(c, sigma, tensor_cores):
+    """Interior (sigma 0.01, 0.1), MLR-projection branch (0.3) and expmap clip (1.0) at the BASELINE channel count,
+    on both contraction paths (tcgen05 3xTF32 and fp32 CUDA cores)."""
     C, O, H, W = 256, 19, 24, 40
     P, A = synth.head_params(O, C, seed=3, dtype=torch.float64)
     u = torch.stack([synth.image_features(i, C, H, W, sigma=sigma) for i in range(2)])
     logits, x, rad = ohead.head_forward(u, P, A, c)
     res = halo_b200.head_forward(u.to(DEV), P.to(DEV), A.to(DEV), c, want_logits=True, want_radius=True,
-                                 want_pixunc=True, want_label=True)
+                                 want_pixunc=True, want_label=True, tensor_cores=tensor_cores)
     assert rel_err(res["logits"], logits) <= TOL
     assert rel_err(res["radius"], rad) <= TOL
     p = torch.softmax(logits, dim=1)
@@ -67,6 +70,30 @@ def test_odd_shapes_and_class_counts(shape):
     res = halo_b200.head_forward(u.to(DEV), P.to(DEV), A.to(DEV), 1.0, want_logits=True, want_radius=True)
     assert rel_err(res["logits"], logits) <= TOL
     assert rel_err(res["radius"], rad) <= TOL
+
+
+@pytest.mark.parametrize("shape", [(19, 32, 8, 16, 1), (16, 64, 24, 40, 3), (3, 64, 10, 10, 1), (32, 128, 9, 12, 2),
+                                   (19, 256, 130, 126, 2), (19, 64, 160, 320, 1), (8, 96, 31, 36, 2)])
+def test_tensor_core_path_shapes(shape):
+    """tcgen05 path: class counts that pad differently (N = 16/32/48/64 columns), several channel counts (1-8
+    pipeline stages), tiles that straddle the end of an image (H*W % 128 != 0) and many tiles per CTA."""
+    O, C, H, W, N = shape
+    P, A = synth.head_params(O, C, seed=9, dtype=torch.float64)
+    u = torch.stack([synth.image_features(i, C, H, W, sigma=0.2) for i in range(N)])
+    gt = torch.stack([synth.image_labels(i, O, H, W) for i in range(N)])
+    logits, x, rad = ohead.head_forward(u, P, A, 1.0)
+    tc = halo_b200.head_forward(u.to(DEV), P.to(DEV), A.to(DEV), 1.0, want_logits=True, want_radius=True, want_pixunc=True,
+                                want_label=True, want_stats=True, gt=gt.to(DEV), pixunc_mode="one_minus_pgt",
+                                label_mode="gt_filled")
+    cc = halo_b200.head_forward(u.to(DEV), P.to(DEV), A.to(DEV), 1.0, want_logits=True, want_radius=True, want_pixunc=True,
+                                want_label=True, want_stats=True, gt=gt.to(DEV), pixunc_mode="one_minus_pgt",
+                                label_mode="gt_filled", tensor_cores=False)
+    assert rel_err(tc["logits"], logits) <= TOL
+    assert rel_err(tc["radius"], rad) <= TOL
+    assert torch.equal(tc["radius"], cc["radius"])                 # |u|^2 is accumulated in the same order on both paths
+    assert torch.allclose(tc["stats"][:, :2], cc["stats"][:, :2])
+    assert rel_err(tc["pixunc"], cc["pixunc"]) <= 1e-4
+    assert (tc["label"] == cc["label"]).float().mean().item() >= 0.999
 
 
 def test_points_outside_and_zero_features():
