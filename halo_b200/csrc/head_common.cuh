@@ -64,6 +64,14 @@ static __global__ void head_pack_kernel(const float* __restrict__ P, const float
 
 
 // ---- per-pixel epilogue (shared by every head kernel) ---------------------------------------------------
+// single-MUFU approximations (flush-to-zero, no denormal/range fix-up code around them); every argument they
+// see in the epilogue is a normal number by construction (D >= 1e-12, p + 1e-6, x^2 + 1 ...)
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_ln(float x) { return fast_lg2(x) * 0.69314718056f; }
+__device__ __forceinline__ float fast_exp(float x) { return fast_ex2(x * 1.44269504089f); }
 struct PixelScalars {
   float gamma;   // x = gamma * u
   float t2;      // c*|x|^2
@@ -72,19 +80,23 @@ struct PixelScalars {
   float xnorm;   // |x|
 };
 
-// raw features: expmap0 + project fused (hyperbolic.py:37-38 with geoopt's fp64 eps 1e-5).  Once per pixel,
-// so the accurate libm versions are affordable.
+// raw features: expmap0 + project fused (hyperbolic.py:37-38 with geoopt's fp64 eps 1e-5).  Branch-free.
 __device__ __forceinline__ PixelScalars tangent_scalars(float n2, const HeadConsts& hc) {
   PixelScalars ps;
-  const float n = sqrtf(n2);
+  const float n = n2 * fast_rsqrt(fmaxf(n2, 1e-30f));  // sqrt(n2), 0 at the origin
   const float sn = hc.s * n;
   const bool clipped = sn > hc.z_clip;  // tanh(min(sn,15)) > 1-1e-5
   const float z = fminf(sn, hc.z_clip);
-  const float e = expf(-2.f * z);
-  const float t = clipped ? hc.t_clip : tanhf(z);
+  const float e = fast_exp(-2.f * z);
   const float ope = 1.f + e;
-  ps.omega = clipped ? hc.omega_clip : 4.f * e / (ope * ope);  // sech^2(z): never form 1 - t^2
-  ps.gamma = t / (hc.s * fmaxf(n, 1e-15f));
+  const float inv_ope = fast_rcp(ope);
+  // tanh: odd series below 0.1 (1 - e would cancel), (1-e)/(1+e) above
+  const float z2 = z * z;
+  const float t_small = z * fmaf(z2, fmaf(z2, fmaf(z2, -17.f / 315.f, 2.f / 15.f), -1.f / 3.f), 1.f);
+  const float t_big = (1.f - e) * inv_ope;
+  const float t = clipped ? hc.t_clip : (z < 0.1f ? t_small : t_big);
+  ps.omega = clipped ? hc.omega_clip : 4.f * e * inv_ope * inv_ope;  // sech^2(z): never form 1 - t^2
+  ps.gamma = t * fast_rcp(hc.s * fmaxf(n, 1e-15f));
   ps.t2 = t * t;
   ps.radius = hc.two_over_s * z;
   ps.xnorm = t * hc.inv_s;
@@ -104,15 +116,18 @@ __device__ __forceinline__ PixelScalars ball_scalars(double n2, const HeadConsts
   return ps;
 }
 
-// asinh through the SFU: sign(x) * ln(|x| + sqrt(x^2+1)); absolute error ~2e-7, which the logit tolerance
-// (1e-5 of max|logit|) absorbs with a wide margin (DESIGN.md "K1 numerics").
+// asinh through the SFU, branch-free: sign(x) * ln(|x| + sqrt(x^2+1)); absolute error ~2e-7, which the logit
+// tolerance (1e-5 of max|logit|) absorbs with a wide margin (DESIGN.md "K1 numerics").
 __device__ __forceinline__ float fast_asinh(float x) {
   const float ax = fabsf(x);
-  const float r = (ax > 1e8f) ? (__logf(ax) + 0.69314718f) : __logf(ax + sqrtf(fmaf(ax, ax, 1.f)));
-  return copysignf(r, x);
+  const float v = fmaf(ax, ax, 1.f);
+  const float r_mid = fast_ln(ax + v * fast_rsqrt(v));
+  const float r_big = fast_ln(ax) + 0.69314718f;  // x^2 overflows beyond ~1.8e19
+  return copysignf(ax > 1e9f ? r_big : r_mid, x);
 }
 
-// HyperMLR logit for one class from the two contractions (hyperbolic.py:146-183)
+// HyperMLR logit for one class from the two contractions (hyperbolic.py:146-183).  Both branches of the
+// MLR-ball projection are evaluated and selected (no divergence inside the warp).
 __device__ __forceinline__ float mlr_logit(float S, float T, const PixelScalars& ps, float pp, float an, float pa,
                                            float Bk, const HeadConsts& hc) {
   const float px = ps.gamma * S;
@@ -122,15 +137,14 @@ __device__ __forceinline__ float mlr_logit(float S, float T, const PixelScalars&
   const float D = fmaxf(fmaf(hc.c * ps.t2, pp, 1.f + cpx2), 1e-12f);      // :152-153
   const float num = fmaf(Bk, xa, Anum * pa);                              // D * <(-p)(+)x, a_hat>   (:175-177)
   const float bo = Bk * ps.omega;
-  const float invD = __fdividef(1.f, D);
+  const float invD = fast_rcp(D);
   const float omc = bo * invD;                                            // 1 - c*|(-p)(+)x|^2
-  float arg;
-  if (omc >= hc.om_max) {
-    arg = __fdividef(hc.two_s * num, fmaxf(bo, 1e-12f * D));              // inside the MLR ball: D cancels (:179-180)
-  } else {
-    const float m = fmaxf(1.f - omc, 0.f) * hc.inv_c;                     // |(-p)(+)x|^2
-    arg = num * invD * hc.out_scale * rsqrtf(fmaxf(m, 1e-24f));           // projected to maxnorm (:162-170)
-  }
+  // inside the MLR ball: D cancels (:179-180)
+  const float arg_in = hc.two_s * num * fast_rcp(fmaxf(bo, 1e-12f * D));
+  // outside: projected to maxnorm (:162-170)
+  const float m = fmaxf(1.f - omc, 0.f) * hc.inv_c;                       // |(-p)(+)x|^2
+  const float arg_out = num * invD * hc.out_scale * fast_rsqrt(fmaxf(m, 1e-24f));
+  const float arg = (omc >= hc.om_max) ? arg_in : arg_out;
   return hc.two_over_s * an * fast_asinh(arg);                            // :181-183 (lambda_term = 2.0)
 }
 
@@ -147,19 +161,19 @@ __device__ __forceinline__ void softmax_stats(const float (&l)[OP], int O, const
   float Z = 0.f;
 #pragma unroll
   for (int k = 0; k < OP; ++k) {
-    e[k] = (k < O) ? __expf(l[k] - mx) : 0.f;
+    e[k] = (k < O) ? fast_exp(l[k] - mx) : 0.f;
     Z += e[k];
   }
-  const float iz = __fdividef(1.f, Z);
+  const float iz = fast_rcp(Z);
   const int gtf = (gt == 255) ? arg : gt;
   if (pixunc_mode == HALO_PIXUNC_ENTROPY) {
     float ent = 0.f;
 #pragma unroll
     for (int k = 0; k < OP; ++k) {
       const float p = e[k] * iz;
-      if (k < O) ent -= p * __logf(p + 1e-6f);
+      if (k < O) ent -= p * fast_lg2(p + 1e-6f);
     }
-    pixunc = ent * hc.inv_log19;
+    pixunc = ent * (0.69314718056f * hc.inv_log19);
   } else {
     float pg = 0.f;
 #pragma unroll

@@ -88,11 +88,10 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ uint32_t cvt_rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// round-to-nearest (ties away) to TF32 with two integer ops; ptxas expands cvt.rna.tf32.f32 into ~6 instructions
+// on sm_100a (profiles/r1_k1_tc.md).  Sign-magnitude bits: adding half an ulp of the 10-bit mantissa to the
+// magnitude and clearing the 13 low bits rounds correctly for both signs (inf/NaN inputs stay non-finite).
+__device__ __forceinline__ uint32_t cvt_rna_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -182,8 +181,8 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     const float4* src = reinterpret_cast<const float4*>(wtc);
     float4* dst = reinterpret_cast<float4*>(sW);
     for (int i = threadIdx.x; i < n4; i += TC_THREADS) dst[i] = src[i];
-    const float* csrc = wtc + (size_t)2 * NP * C;
-    for (int i = threadIdx.x; i < 4 * OP; i += TC_THREADS) sCls[i] = csrc[i];
+    const float* csrc = wtc + (size_t)2 * NP * C;  // [4][OP] -> per-class float4 {pp, an, pa, Bk}
+    for (int i = threadIdx.x; i < 4 * OP; i += TC_THREADS) sCls[(i % OP) * 4 + i / OP] = csrc[i];
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -326,17 +325,14 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       for (int qa = 0; qa < NACC; ++qa) {
         if (qa < cpt || qa == NMAIN) {  // main accumulators that received no stage (C < NMAIN*32) hold garbage
           const uint32_t taddr = tmem_base + lane_addr + TC_ACC_COL0 + (g * NACC + qa) * NP;
-          float buf[8];
+          float buf[2 * OP];
 #pragma unroll
-          for (int c8 = 0; c8 < (2 * OP) / 8; ++c8) {
-            tmem_ld_x8(taddr + c8 * 8, buf);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          for (int c8 = 0; c8 < (2 * OP) / 8; ++c8) tmem_ld_x8(taddr + c8 * 8, *reinterpret_cast<float(*)[8]>(&buf[c8 * 8]));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int col = c8 * 8 + e;
-              if (col < OP) S[col] += buf[e];
-              else T[col - OP] += buf[e];
-            }
+          for (int col = 0; col < 2 * OP; ++col) {
+            if (col < OP) S[col] += buf[col];
+            else T[col - OP] += buf[col];
           }
         }
       }
@@ -348,8 +344,10 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       const PixelScalars ps = tangent_scalars(n2, hc);
       float l[OP];
 #pragma unroll
-      for (int k = 0; k < OP; ++k)
-        l[k] = mlr_logit(S[k], T[k], ps, sCls[k], sCls[OP + k], sCls[2 * OP + k], sCls[3 * OP + k], hc);
+      for (int k = 0; k < OP; ++k) {
+        const float4 cl = reinterpret_cast<const float4*>(sCls)[k];
+        l[k] = mlr_logit(S[k], T[k], ps, cl.x, cl.y, cl.z, cl.w, hc);
+      }
 #ifdef HALO_TC_VARIANTS
       if (a.debug_raw) {  // numerics probe: expose the raw contractions <u,a_hat_k> instead of the logits
 #pragma unroll

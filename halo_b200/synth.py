@@ -47,10 +47,11 @@ def image_labels(index, O, H, W, seed=1234, device="cpu", ignore_frac=0.05):
 def batch(lo, hi, C, O, H, W, sigma=0.1, seed=1234, device="cpu"):
     """Round-1 state for pool images [lo, hi): dict(feat, gt, active, selected, active_mask)."""
     n = hi - lo
-    feat = torch.stack([image_features(i, C, H, W, sigma, seed, device) for i in range(lo, hi)]) if n else \
-        torch.empty((0, C, H, W), device=device)
-    gt = torch.stack([image_labels(i, O, H, W, seed, device) for i in range(lo, hi)]) if n else \
-        torch.empty((0, H, W), dtype=torch.uint8, device=device)
+    feat = torch.empty((n, C, H, W), dtype=torch.float32, device=device)  # filled in place: a pool batch can be > 100 GB
+    gt = torch.empty((n, H, W), dtype=torch.uint8, device=device)
+    for k, i in enumerate(range(lo, hi)):
+        feat[k] = image_features(i, C, H, W, sigma, seed, device)
+        gt[k] = image_labels(i, O, H, W, seed, device)
     return dict(
         feat=feat, gt=gt,
         active=torch.zeros((n, H, W), dtype=torch.uint8, device=device),
