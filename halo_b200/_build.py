@@ -41,18 +41,31 @@ def build(force=False, verbose=False, extra_flags=None):
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     procs = []
+    extra = list(extra_flags or os.environ.get("HALO_EXTRA_NVCC", "").split())
+    stamp = os.path.join(objdir, "flags.txt")
+    flags_changed = (not os.path.exists(stamp)) or open(stamp).read() != " ".join(NVCC_FLAGS + extra)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")] + \
+        [os.path.join(HERE, "..", "include", "halo_b200.h")]
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    up_to_date = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
-        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags or os.environ.get("HALO_EXTRA_NVCC", "").split()) + ["-c", src, "-o", obj]
+        if (not force and not flags_changed and os.path.exists(obj)
+                and os.path.getmtime(obj) > max(os.path.getmtime(src), newest_header)):
+            up_to_date.append(obj)  # incremental: only recompile what changed
+            continue
+        cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", src, "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    objs, logs = [], []
+    objs, logs = list(up_to_date), []
     for src, obj, p in procs:
         out, _ = p.communicate()
         logs.append(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, out))
         objs.append(obj)
-    with open(os.path.join(objdir, "ptxas.log"), "w") as f:
+    with open(stamp, "w") as f:
+        f.write(" ".join(NVCC_FLAGS + extra))
+    with open(os.path.join(objdir, "ptxas.log"), "a" if up_to_date else "w") as f:
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))

@@ -60,7 +60,7 @@ def load(build_if_missing=True):
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB
+        path = os.environ.get("HALO_B200_LIB", _build.LIB)  # override: A/B experiments with differently built libraries
         if not os.path.exists(path):
             if not build_if_missing:
                 raise RuntimeError("libhalo_sm100.so is missing: run `python -m halo_b200._build`")

@@ -15,7 +15,8 @@
 //                         accumulate |u|^2, split hi/lo, tcgen05.st both into the A-operand columns of TMEM;
 //                       * epilogue: tcgen05.ld the 2*OP accumulator columns of the pixel and run the same
 //                         register epilogue as the CUDA-core kernel (Mobius algebra, asinh, radius, softmax entropy).
-//   warp 1 (1 lane)   MMA issuer: tcgen05.mma.kind::tf32, M=128 (pixels) x N=NP (2*OP padded to 16) x K=8,
+//   warps 1, 3        MMA issuers (1 lane each, one per pixel warpgroup): tcgen05.mma.kind::tf32, M=128 (pixels) x
+//                     N=NP (2*OP padded to 16) x K=8,
 //                     A from TMEM, B (class parameters, hi and lo planes) from shared memory, D in TMEM;
 //                     tcgen05.commit releases A buffers / publishes accumulators through mbarriers.
 // The class parameters (<= 96 KB) stay resident in shared memory for the life of the CTA.
@@ -29,7 +30,10 @@ namespace halo {
 
 constexpr int TC_BM = 128;      // pixels per tile = MMA M = TMEM lanes
 constexpr int TC_BK = 32;       // channels per pipeline stage
-constexpr int TC_WG_STAGES = 3;  // shared-memory stages per pixel warpgroup (each warpgroup has its own ring + producer)
+#ifndef HALO_TC_WG_STAGES
+#define HALO_TC_WG_STAGES 3
+#endif
+constexpr int TC_WG_STAGES = HALO_TC_WG_STAGES;  // shared-memory stages per pixel warpgroup (each warpgroup has its own ring + producer)
 constexpr int TC_STAGES = TC_WG_STAGES * 2;
 constexpr int TC_STAGE_FLOATS = TC_BK * TC_BM;
 constexpr int TC_NWG = 2;       // pixel warpgroups
@@ -39,6 +43,10 @@ constexpr int TC_HK = 16;       // channels per A-operand half-buffer (two per p
 constexpr int TC_ACOLS = 2 * TC_HK;                 // per A half-buffer: 16 hi + 16 lo columns
 constexpr int TC_ACC_COL0 = TC_NWG * 2 * TC_ACOLS;  // = 128: accumulators start after the A buffers
 constexpr int TC_NACC_MAX = 4;  // partial accumulators per tile (shortens the in-TMEM accumulation chains)
+
+// i-th tile of CTA b (G CTAs): the NWG warpgroups of a CTA take ADJACENT 128-pixel tiles (2b, 2b+1, then +2G ...), so a
+// CTA reads 1 KB runs of every channel row within a short window and neighbouring CTAs continue the same DRAM pages.
+__device__ __forceinline__ int tc_tile_of(int i, int b, int G) { return (i / TC_NWG) * (TC_NWG * G) + b * TC_NWG + (i % TC_NWG); }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -212,7 +220,14 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
 
   const int HW = a.HW;
   const int cpt = C / TC_BK;  // chunks (pipeline stages) per tile
-  const int my_tiles = (blockIdx.x < a.total_tiles) ? (a.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // number of i with tc_tile_of(i) < total_tiles: full rounds of NWG tiles plus the tail of the last round
+  int my_tiles = 0;
+  {
+    const int per_round = TC_NWG * gridDim.x;
+    const int rounds = a.total_tiles / per_round, rem = a.total_tiles - rounds * per_round;
+    const int tail = rem - (int)blockIdx.x * TC_NWG;
+    my_tiles = rounds * TC_NWG + (tail <= 0 ? 0 : (tail >= TC_NWG ? TC_NWG : tail));
+  }
 
   if (warp == 0 || warp == 2) {
     // =================== TMA producers: warp 0 feeds warpgroup 0, warp 2 feeds warpgroup 1 ===================
@@ -222,7 +237,7 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     if (lane == 0) {
       for (int i = g; i < my_tiles; i += TC_NWG) {
         const int it = i / TC_NWG;
-        const int tile = blockIdx.x + i * gridDim.x;
+        const int tile = tc_tile_of(i, blockIdx.x, gridDim.x);
         const int n = tile / a.tiles_per_img;
         const int p0 = (tile - n * a.tiles_per_img) * TC_BM;
         for (int j = 0; j < cpt; ++j) {
@@ -236,21 +251,25 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // =================== MMA issuer ===================
+  } else if (warp == 1 || warp == 3) {
+    // =================== MMA issuers: warp 1 serves warpgroup 0, warp 3 serves warpgroup 1 ===================
+    // One issuing thread per pixel warpgroup, each strictly in order for ITS warpgroup: the two conversion
+    // streams then overlap on the tensor pipe instead of being serialised behind a single in-order issuer
+    // (tcgen05.commit tracks the MMAs of the executing thread only, and the two streams touch disjoint TMEM).
+    const int g = warp >> 1;
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N=NP, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + (size_t)NP * C);
       const uint32_t lbo = NP * 16, sbo = 128;
-      for (int i = 0; i < my_tiles; ++i) {
-        const int g = i % TC_NWG, it = i / TC_NWG;
+      const uint32_t d_corr = tmem_base + TC_ACC_COL0 + (g * NACC + NMAIN) * NP;
+      for (int i = g; i < my_tiles; i += TC_NWG) {
+        const int it = i / TC_NWG;
         mbar_wait(&acc_empty[g], ((uint32_t)it & 1u) ^ 1u);
         tc_fence_after();
         for (int j = 0; j < cpt; ++j) {
           const int ca = it * cpt + j;                      // stage counter of this warpgroup
           const uint32_t d_main = tmem_base + TC_ACC_COL0 + (g * NACC + (j % NMAIN)) * NP;
-          const uint32_t d_corr = tmem_base + TC_ACC_COL0 + (g * NACC + NMAIN) * NP;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             mbar_wait(&a_full[g * 2 + h], (uint32_t)ca & 1u);
@@ -282,7 +301,7 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     const HeadConsts hc = a.hc;
     for (int i = g; i < my_tiles; i += TC_NWG) {
       const int it = i / TC_NWG;
-      const int tile = blockIdx.x + i * gridDim.x;
+      const int tile = tc_tile_of(i, blockIdx.x, gridDim.x);
       const int n = tile / a.tiles_per_img;
       const int p = (tile - n * a.tiles_per_img) * TC_BM + m;
       float n2 = 0.f;
@@ -492,7 +511,7 @@ int head_fwd_tc_launch(HeadArgs a, const float* std_pack, float* wtc, cudaStream
   a.total_tiles = a.tiles_per_img * a.N;
   const TcSmemLayout L = tc_smem_layout(NP, OP, a.C);
   int grid = sm_count();
-  if (grid > a.total_tiles) grid = a.total_tiles;
+  if (grid > (a.total_tiles + TC_NWG - 1) / TC_NWG) grid = (a.total_tiles + TC_NWG - 1) / TC_NWG;
   switch (OP) {
     case 4: return launch_tc<16, 4>(tmap, a, wtc, L.total, grid, st);
     case 8: return launch_tc<16, 8>(tmap, a, wtc, L.total, grid, st);
