@@ -103,9 +103,25 @@ struct SelShared {
   unsigned total;
   unsigned cnt;
   int npicks;
+  int grp_p[32];  // pixel index of the picks of the current group, in pick order
 };
 
-template <typename S>
+// address-space-specific accessors of the suppression bitmap: shared-memory atomics (ATOMS) when it fits next to the
+// candidate list, global atomics otherwise -- a generic pointer would make every mark a slow generic ATOM
+template <bool GBM>
+struct Bitmap {
+  unsigned* base;  // shared (GBM=false) or global (GBM=true)
+  __device__ __forceinline__ bool test(int p) const {
+    if (GBM) return (__ldcg(base + (p >> 5)) >> (p & 31)) & 1u;
+    return (*(volatile unsigned*)(base + (p >> 5)) >> (p & 31)) & 1u;
+  }
+  __device__ __forceinline__ void set_bits(int word, unsigned msk) const {
+    if (GBM) atomicOr(base + word, msk);
+    else atomicOr(reinterpret_cast<unsigned*>(__cvta_shared_to_generic(__cvta_generic_to_shared(base + word))), msk);
+  }
+};
+
+template <typename S, bool GBM>
 __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const SelArgs<S> a) {
   typedef SelTraits<S> TR;
   typedef typename TR::Comp Comp;
@@ -118,7 +134,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const SelArgs<S>
   const int H = a.H, W = a.W, HW = H * W, LB = a.LB, TB = TR::KB + LB;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   S* score = a.score + (size_t)img * HW;
-  unsigned* bitmap = a.gbitmap ? a.gbitmap + (size_t)img * a.words : sbitmap;
+  unsigned* bitmap = GBM ? a.gbitmap + (size_t)img * a.words : sbitmap;
+  const Bitmap<GBM> bm{bitmap};
   int* picks = a.picks + (size_t)img * a.n_regions;
   const Comp lin_mask = (((Comp)1) << LB) - 1;
   const unsigned LINMAX = (unsigned)(HW - 1);
@@ -241,11 +258,12 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const SelArgs<S>
           const int w = (int)(lin / (unsigned)H), h = (int)(lin - (unsigned)w * H);
           const int p = h * W + w;
           picks[npicks + i] = p;
-          atomicOr(&bitmap[p >> 5], 1u << (p & 31));
+          bm.set_bits(p >> 5, 1u << (p & 31));
         }
         npicks += take;
       } else {
         for (int base = 0; base < cnt && npicks < a.n_regions; base += 32) {
+          // lane i holds the i-th best remaining candidate of this group
           const int i = base + lane;
           int h = -1000000, w = -1000000;
           bool alive = false;
@@ -253,30 +271,57 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const SelArgs<S>
             const unsigned lin = LINMAX - (unsigned)(list[i] & lin_mask);
             w = (int)(lin / (unsigned)H);
             h = (int)(lin - (unsigned)w * H);
-            const int p = h * W + w;
-            alive = !((*(volatile unsigned*)&bitmap[p >> 5] >> (p & 31)) & 1u);
+            alive = !bm.test(h * W + w);           // not inside the window of a pick of an earlier group
           }
-          unsigned live = __ballot_sync(0xffffffffu, alive);
-          while (live != 0u && npicks < a.n_regions) {
-            const int j = __ffs(live) - 1;
+          const unsigned alive_mask = __ballot_sync(0xffffffffu, alive);
+          if (alive_mask == 0u) continue;
+          // conflict mask: earlier lanes of the group within Chebyshev distance m
+          unsigned conf = 0u;
+#pragma unroll 8
+          for (int j = 0; j < 31; ++j) {
             const int hj = __shfl_sync(0xffffffffu, h, j), wj = __shfl_sync(0xffffffffu, w, j);
-            if (lane == 0) picks[npicks] = hj * W + wj;
-            ++npicks;
-            // mark the (2m+1)^2 window, one lane per row
-            const int x0 = max(wj - m, 0), x1 = min(wj + m, W - 1);
-            for (int ry = lane; ry <= 2 * m; ry += 32) {
-              const int y = hj - m + ry;
-              if (y < 0 || y >= H) continue;
-              const int p0 = y * W + x0, p1 = y * W + x1;
-              for (int wd = p0 >> 5; wd <= (p1 >> 5); ++wd) {
-                const int blo = max(p0 - (wd << 5), 0), bhi = min(p1 - (wd << 5), 31);
-                const unsigned msk = (bhi == 31 ? 0xffffffffu : ((1u << (bhi + 1)) - 1u)) & ~((1u << blo) - 1u);
-                atomicOr(&bitmap[wd], msk);
-              }
-            }
-            if (alive && abs(h - hj) <= m && abs(w - wj) <= m) alive = false;
-            live = __ballot_sync(0xffffffffu, alive);
+            if (j < lane && abs(h - hj) <= m && abs(w - wj) <= m) conf |= 1u << j;
           }
+          // resolve in order (identical in every lane): picked iff alive and no earlier PICKED lane conflicts
+          unsigned picked = 0u;
+          unsigned todo = alive_mask;
+          while (todo) {
+            const int j = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const unsigned cj = __shfl_sync(0xffffffffu, conf, j);
+            if ((cj & picked) == 0u) picked |= 1u << j;
+          }
+          // budget: keep only the first (n_regions - npicks) picks of the group
+          const int room = a.n_regions - npicks;
+          if (__popc(picked) > room) {
+            unsigned keep = 0u, t = picked;
+            for (int r = 0; r < room; ++r) { keep |= t & (0u - t); t &= t - 1; }
+            picked = keep;
+          }
+          const int npk = __popc(picked);
+          if ((picked >> lane) & 1u) {
+            const int rank = __popc(picked & ((1u << lane) - 1u));
+            picks[npicks + rank] = h * W + w;
+            sh.grp_p[rank] = h * W + w;
+          }
+          __syncwarp();
+          // mark the (2m+1)^2 windows of all picks of the group: (pick, row) tasks spread over the lanes
+          const int rows = 2 * m + 1;
+          for (int t = lane; t < npk * rows; t += 32) {
+            const int k = t / rows, ry = t - k * rows;
+            const int pj = sh.grp_p[k];
+            const int hj = pj / W, wj = pj - hj * W;
+            const int y = hj - m + ry;
+            if (y < 0 || y >= H) continue;
+            const int x0 = max(wj - m, 0), x1 = min(wj + m, W - 1);
+            const int p0 = y * W + x0, p1 = y * W + x1;
+            for (int wd = p0 >> 5; wd <= (p1 >> 5); ++wd) {
+              const int blo = max(p0 - (wd << 5), 0), bhi = min(p1 - (wd << 5), 31);
+              const unsigned msk = (bhi == 31 ? 0xffffffffu : ((1u << (bhi + 1)) - 1u)) & ~((1u << blo) - 1u);
+              bm.set_bits(wd, msk);
+            }
+          }
+          npicks += npk;
           __syncwarp();
         }
       }
@@ -366,8 +411,13 @@ static int select_launch(S* score, uint8_t* active, uint8_t* selected, uint8_t* 
   } else {
     a.gbitmap = (unsigned*)((unsigned char*)ws + picks_bytes);
   }
-  HALO_CUDA(cudaFuncSetAttribute(select_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  select_kernel<S><<<N, SEL_THREADS, smem, (cudaStream_t)stream>>>(a);
+  if (a.gbitmap) {
+    HALO_CUDA(cudaFuncSetAttribute(select_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    select_kernel<S, true><<<N, SEL_THREADS, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    HALO_CUDA(cudaFuncSetAttribute(select_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    select_kernel<S, false><<<N, SEL_THREADS, smem, (cudaStream_t)stream>>>(a);
+  }
   return launch_status("select_kernel");
 }
 
