@@ -6,15 +6,17 @@
 // split u = hi + lo (both TF32-representable, round-to-nearest) and three MMAs accumulate in fp32:
 //        D += U_hi.W_hi + U_lo.W_hi + U_hi.W_lo            (the dropped lo.lo term is ~2^-22 relative)
 //
-// Pipeline of one persistent CTA (one per SM, 384 threads):
+// Pipeline of one persistent CTA (one per SM, 512 threads):
 //   warps 0, 2        TMA producers (1 lane each, one per pixel warpgroup): [32 channels x 128 pixels] fp32 boxes of
 //                     the NCHW feature tensor (viewed as a 2-D [N*C, H*W] tensor) into that warpgroup's 3-deep
 //                     shared-memory ring (16 KB per stage), completion by mbarrier tx-count.
-//   warps 4-7, 8-11   two "pixel" warpgroups working on alternate 128-pixel tiles; thread = pixel = TMEM lane:
-//                       * convert: read the pixel's 32 channel values of a stage (conflict-free, pixels contiguous),
-//                         accumulate |u|^2, split hi/lo, tcgen05.st both into the A-operand columns of TMEM;
-//                       * epilogue: tcgen05.ld the 2*OP accumulator columns of the pixel and run the same
-//                         register epilogue as the CUDA-core kernel (Mobius algebra, asinh, radius, softmax entropy).
+//   warps 4-7, 8-11   two CONVERTER warpgroups working on alternate (adjacent) 128-pixel tiles; thread = pixel = TMEM
+//                     lane: read the pixel's channel values of a stage (conflict-free, pixels contiguous), accumulate
+//                     |u|^2, split hi/lo, tcgen05.st both into the A-operand columns of TMEM.
+//   warps 12-15       EPILOGUE warpgroup, every tile in order: tcgen05.ld the accumulator columns of the pixel and run
+//                     the same register epilogue as the CUDA-core kernel (Mobius algebra, asinh, radius, softmax
+//                     entropy); the converters never wait for it (profiles/r1_k1_tc.md: a warpgroup that converts AND
+//                     finishes its tile leaves the SM issue slots half empty).
 //   warps 1, 3        MMA issuers (1 lane each, one per pixel warpgroup): tcgen05.mma.kind::tf32, M=128 (pixels) x
 //                     N=NP (2*OP padded to 16) x K=8,
 //                     A from TMEM, B (class parameters, hi and lo planes) from shared memory, D in TMEM;
@@ -36,8 +38,8 @@ constexpr int TC_BK = 32;       // channels per pipeline stage
 constexpr int TC_WG_STAGES = HALO_TC_WG_STAGES;  // shared-memory stages per pixel warpgroup (each warpgroup has its own ring + producer)
 constexpr int TC_STAGES = TC_WG_STAGES * 2;
 constexpr int TC_STAGE_FLOATS = TC_BK * TC_BM;
-constexpr int TC_NWG = 2;       // pixel warpgroups
-constexpr int TC_THREADS = 128 + 128 * TC_NWG;
+constexpr int TC_NWG = 2;       // converter warpgroups (each owns a TMA ring, an MMA issuer, A buffers and accumulators)
+constexpr int TC_THREADS = 128 + 128 * TC_NWG + 128;  // control warps + converters + one epilogue warpgroup
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_HK = 16;       // channels per A-operand half-buffer (two per pipeline stage)
 constexpr int TC_ACOLS = 2 * TC_HK;                 // per A half-buffer: 16 hi + 16 lo columns
@@ -139,7 +141,7 @@ __device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr, uint32_t lbo
 }
 
 struct TcSmemLayout {
-  size_t w_bytes, ring_off, bar_off, tmem_off, cls_off, total;
+  size_t w_bytes, ring_off, bar_off, tmem_off, cls_off, n2_off, total;
 };
 __host__ __device__ inline TcSmemLayout tc_smem_layout(int NP, int OP, int C) {
   TcSmemLayout L;
@@ -149,7 +151,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int NP, int OP, int C) {
   const int nbars = 2 * TC_STAGES + TC_NWG * 2 * 2 + TC_NWG * 2;
   L.tmem_off = L.bar_off + (size_t)nbars * 8;
   L.cls_off = (L.tmem_off + 16 + 15) / 16 * 16;
-  L.total = L.cls_off + (size_t)4 * OP * 4;
+  L.n2_off = L.cls_off + (size_t)4 * OP * 4;
+  L.total = L.n2_off + (size_t)TC_NWG * TC_BM * 4;  // |u|^2 of the tile each converter warpgroup just finished
   return L;
 }
 
@@ -180,6 +183,7 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
   uint64_t* acc_empty = acc_full + TC_NWG;               // [NWG]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
   float* sCls = reinterpret_cast<float*>(smem + L.cls_off);
+  float* sN2 = reinterpret_cast<float*>(smem + L.n2_off);  // [NWG][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -292,18 +296,14 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {
-    // =================== pixel warpgroups: convert + epilogue ===================
+  } else if (warp >= 4 && warp < 4 + 4 * TC_NWG) {
+    // =================== converter warpgroups (thread = pixel = TMEM lane) ===================
     const int g = (warp - 4) >> 2;
     const int wq = warp & 3;                   // TMEM lane quarter this warp may touch
     const int m = wq * 32 + lane;              // pixel row inside the tile
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    const HeadConsts hc = a.hc;
     for (int i = g; i < my_tiles; i += TC_NWG) {
       const int it = i / TC_NWG;
-      const int tile = tc_tile_of(i, blockIdx.x, gridDim.x);
-      const int n = tile / a.tiles_per_img;
-      const int p = (tile - n * a.tiles_per_img) * TC_BM + m;
       float n2 = 0.f;
       for (int j = 0; j < cpt; ++j) {
         const int ca = it * cpt + j;                        // stage counter of this warpgroup
@@ -326,6 +326,9 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
           const uint32_t taddr = tmem_base + lane_addr + (g * 2 + h) * TC_ACOLS;
           tmem_st_x16(taddr, hi);
           tmem_st_x16(taddr + TC_HK, lo);
+          // |u|^2 travels to the epilogue warpgroup through shared memory; it is published by the release of the
+          // tile's last a_full arrival (-> MMA issuer -> tcgen05.commit -> acc_full acquire in the epilogue)
+          if (j == cpt - 1 && h == 1) sN2[g * TC_BM + m] = n2;
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
@@ -333,9 +336,21 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
         }
         if (lane == 0) mbar_arrive(&empty[s]);
       }
-      // ---- epilogue: accumulators of this pixel ----
+    }
+  } else if (warp >= 4 + 4 * TC_NWG) {
+    // =================== epilogue warpgroup: every tile, in order ===================
+    const int wq = warp & 3;
+    const int m = wq * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    const HeadConsts hc = a.hc;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int g = i % TC_NWG, it = i / TC_NWG;
+      const int tile = tc_tile_of(i, blockIdx.x, gridDim.x);
+      const int n = tile / a.tiles_per_img;
+      const int p = (tile - n * a.tiles_per_img) * TC_BM + m;
       mbar_wait(&acc_full[g], (uint32_t)it & 1u);
       tc_fence_after();
+      const float n2 = sN2[g * TC_BM + m];
       float S[OP], T[OP];
 #pragma unroll
       for (int k = 0; k < OP; ++k) S[k] = T[k] = 0.f;
