@@ -158,26 +158,65 @@ __global__ void __launch_bounds__(SC_THREADS) score_pass_a_kernel(const ScoreArg
   }
 }
 
-// Pass B: 4 pixels per thread when the plane is 16-byte friendly
+// Pass B, 4 pixels per thread (planes are 16-byte aligned and H*W % 4 == 0 in the vector variant).
+// normalize: 0 = off; 1 = on, the two maps are normalised in place (what the reference returns);
+//            2 = on, maps left as pass A wrote them (the acquisition path only needs the score: saves 4-8 B/px)
+template <bool VEC4>
 __global__ void score_pass_b_kernel(const ScoreArgs a, long long total) {
   const int HW = a.H * a.W;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
-    const int n = (int)(g / HW);
-    float unc = a.uncertainty[g];
-    float imp = (a.impurity != nullptr) ? a.impurity[g]
-                                        : (a.pur_mode == HALO_PUR_NORM ? a.radius[g] : 0.f);
+  constexpr int V = VEC4 ? 4 : 1;
+  const float ninf = __int_as_float(0xff800000);
+  for (long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * V; g < total; g += (long long)gridDim.x * blockDim.x * V) {
+    const int n = (int)(g / HW);  // the V pixels of a thread never straddle images (HW % 4 == 0 when VEC4)
+    float unc[V], imp[V], sc[V];
+    if (VEC4) {
+      const float4 u4 = *reinterpret_cast<const float4*>(a.uncertainty + g);
+      unc[0] = u4.x; unc[1] = u4.y; unc[2] = u4.z; unc[3] = u4.w;
+      if (a.impurity != nullptr || a.pur_mode == HALO_PUR_NORM) {
+        const float4 i4 = *reinterpret_cast<const float4*>((a.impurity != nullptr ? a.impurity : a.radius) + g);
+        imp[0] = i4.x; imp[1] = i4.y; imp[2] = i4.z; imp[3] = i4.w;
+      } else {
+        imp[0] = imp[1] = imp[2] = imp[3] = 0.f;
+      }
+    } else {
+      unc[0] = a.uncertainty[g];
+      imp[0] = (a.impurity != nullptr) ? a.impurity[g] : (a.pur_mode == HALO_PUR_NORM ? a.radius[g] : 0.f);
+    }
     if (a.normalize) {
       // normalize_map (:22-23): extrema are python floats, the subtraction/division run in the map's dtype
       const float ulo = ord2f(a.mm[4 * n + 0]), uhi = ord2f(a.mm[4 * n + 1]);
       const float ilo = ord2f(a.mm[4 * n + 2]), ihi = ord2f(a.mm[4 * n + 3]);
-      unc = (unc - ulo) / (float)((double)uhi - (double)ulo);
-      imp = (imp - ilo) / (float)((double)ihi - (double)ilo);
-      a.uncertainty[g] = unc;
-      if (a.impurity != nullptr) a.impurity[g] = imp;
+      const float ud = (float)((double)uhi - (double)ulo), id = (float)((double)ihi - (double)ilo);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        unc[e] = (unc[e] - ulo) / ud;
+        imp[e] = (imp[e] - ilo) / id;
+      }
+      if (a.normalize == 1) {
+        if (VEC4) {
+          *reinterpret_cast<float4*>(a.uncertainty + g) = make_float4(unc[0], unc[1], unc[2], unc[3]);
+          if (a.impurity != nullptr) *reinterpret_cast<float4*>(a.impurity + g) = make_float4(imp[0], imp[1], imp[2], imp[3]);
+        } else {
+          a.uncertainty[g] = unc[0];
+          if (a.impurity != nullptr) a.impurity[g] = imp[0];
+        }
+      }
     }
-    float s = imp * unc;
-    if (a.active != nullptr && a.active[g]) s = __int_as_float(0xff800000);
-    a.score[g] = s;
+#pragma unroll
+    for (int e = 0; e < V; ++e) sc[e] = imp[e] * unc[e];
+    if (a.active != nullptr) {
+      if (VEC4) {
+        const uchar4 m4 = *reinterpret_cast<const uchar4*>(a.active + g);
+        if (m4.x) sc[0] = ninf;
+        if (m4.y) sc[1] = ninf;
+        if (m4.z) sc[2] = ninf;
+        if (m4.w) sc[3] = ninf;
+      } else if (a.active[g]) {
+        sc[0] = ninf;
+      }
+    }
+    if (VEC4) *reinterpret_cast<float4*>(a.score + g) = make_float4(sc[0], sc[1], sc[2], sc[3]);
+    else a.score[g] = sc[0];
   }
 }
 
@@ -218,6 +257,7 @@ extern "C" int halo_score(const float* pixunc, const float* radius, const float*
   a.unc_mode = unc_mode; a.pur_mode = pur_mode; a.normalize = normalize; a.k = k; a.pk = pk; a.n_bins = n_bins;
   a.N = N; a.H = H; a.W = W;
   a.inv_log_bins = (n_bins >= 2) ? (float)(1.0 / log((double)n_bins)) : 0.f;
+  HALO_CHECK_ARG(normalize >= 0 && normalize <= 2, "halo_score: normalize must be 0, 1 or 2");
   if (normalize) {
     score_init_kernel<<<(N + 255) / 256, 256, 0, st>>>(a.mm, N);
     int rc = launch_status("score_init_kernel");
@@ -233,8 +273,14 @@ extern "C" int halo_score(const float* pixunc, const float* radius, const float*
   int rc = launch_status("score_pass_a_kernel");
   if (rc) return rc;
   const long long total = (long long)N * H * W;
-  long long blocks = (total + 255) / 256;
-  if (blocks > (long long)sm_count() * 32) blocks = (long long)sm_count() * 32;
-  score_pass_b_kernel<<<(int)blocks, 256, 0, st>>>(a, total);
+  auto aligned = [](const void* q, size_t al) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % al) == 0; };
+  const bool vec4 = ((long long)H * W) % 4 == 0 && aligned(score, 16) && aligned(uncertainty, 16) && aligned(impurity, 16) &&
+                    aligned(radius, 16) && aligned(active, 4);
+  const int V = vec4 ? 4 : 1;
+  long long blocks = (total / V + 255) / 256;
+  if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+  if (blocks < 1) blocks = 1;
+  if (vec4) score_pass_b_kernel<true><<<(int)blocks, 256, 0, st>>>(a, total);
+  else score_pass_b_kernel<false><<<(int)blocks, 256, 0, st>>>(a, total);
   return launch_status("score_pass_b_kernel");
 }

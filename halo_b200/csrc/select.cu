@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const SelArgs<S>
         break;
       }
       const unsigned cum = sh.cum;
-      if (cum > 0 && (cum >= (unsigned)(a.cap / 2) || shift == 0)) {
+      if (cum > 0 && (cum >= (unsigned)(a.cap - a.cap / 8) || shift == 0)) {  // fill the list to >= 7/8 before accepting
         accepted = cum;
         lo = (((prefix << nb) + (Comp)(sel_bin + 1)) << shift);
         break;

@@ -30,7 +30,7 @@ def _reference_cfg(path, default):
 
 
 def score_planes(pixunc, radius, radius_stats, label, active, *, unc_mode, pur_mode, normalize, k, pk, n_bins,
-                 want_impurity=True):
+                 want_impurity=True, want_maps=True):
     """Batched `halo_score` on device planes (N,H,W).  Returns (score, impurity|None, uncertainty)."""
     lib = nat.load()
     ref = pixunc if pixunc is not None else radius
@@ -45,7 +45,7 @@ def score_planes(pixunc, radius, radius_stats, label, active, *, unc_mode, pur_m
     ws = nat.workspace.get(dev, "score", lib.halo_score_workspace_bytes(N))
     with torch.cuda.device(dev):
         rc = lib.halo_score(nat.ptr(pixunc), nat.ptr(radius), nat.ptr(radius_stats), nat.ptr(label), nat.ptr(active),
-                            unc_mode, pur_mode, 1 if normalize else 0, k, pk, n_bins, nat.ptr(score), nat.ptr(imp),
+                            unc_mode, pur_mode, (1 if want_maps else 2) if normalize else 0, k, pk, n_bins, nat.ptr(score), nat.ptr(imp),
                             nat.ptr(unc), N, H, W, nat.ptr(ws), ws.numel(), nat.stream_of(ref))
     nat.check(rc, "halo_score")
     return score, imp, unc

@@ -66,7 +66,7 @@ def acquire_batch(feat, P, A, cfg, gt, active, selected, active_mask, *, want_sc
     n_bins = cfg.K if pur_mode == nat.PUR_RADIUS_BINS else cfg.num_classes
     score, _, _ = score_planes(pixunc, res["radius"], res["stats"], res["label"], active, unc_mode=unc_mode,
                                pur_mode=pur_mode, normalize=cfg.normalize, k=k, pk=pk, n_bins=n_bins,
-                               want_impurity=False)
+                               want_impurity=False, want_maps=False)
     out = {}
     if want_score:
         out["score"] = score.clone()

@@ -120,6 +120,8 @@ int halo_logits_stats(const float* logits, const uint8_t* gt, int pixunc_mode, i
  *   pixunc [N,H,W] f32, radius [N,H,W] f32 (+ its stats [N,4]), label [N,H,W] u8, active [N,H,W] u8|NULL
  *   k = uncertainty window (odd), pk = purity window (odd; 3 when the module was built for "hyper"),
  *   n_bins = class count for LABEL_HIST or K for RADIUS_BINS.
+ *   normalize: 0 = off; 1 = min-max normalise both maps (floating_region.py:206-208) and return them normalised;
+ *              2 = same score, but the impurity/uncertainty planes are left un-normalised (scratch only).
  *   score [N,H,W] f32 (active!=0 -> -inf, build.py:146); impurity / uncertainty [N,H,W] f32 are
  *   REQUIRED scratch+outputs (they receive the maps the reference returns). */
 size_t halo_score_workspace_bytes(int N);
