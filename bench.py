@@ -240,7 +240,7 @@ def run_ours(args):
     gt[torch.rand((B, H, W), generator=g, device=dev) < 0.05] = 255
     total_steps = args.steps + args.warmup
     # fresh round-1 state per step, allocated up front so that no fill kernel runs inside the timed region
-    n_state = min(total_steps, 64)
+    n_state = min(total_steps, 16)
     state = [dict(active=torch.zeros((B, H, W), dtype=torch.uint8, device=dev),
                   selected=torch.zeros((B, H, W), dtype=torch.uint8, device=dev),
                   active_mask=torch.full((B, H, W), 255, dtype=torch.uint8, device=dev)) for _ in range(n_state)]
@@ -408,10 +408,11 @@ def run_e2e(args, cfg, P, A, dev, rank, world, distributed):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="images resident per GPU per step")
+    ap.add_argument("--batch", type=int, default=148,
+                    help="images resident per GPU per step (148 = one selection CTA per SM; 124 GB of features)")
     ap.add_argument("--e2e-batch", type=int, default=4, help="images per end-to-end step (pinned host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -23,6 +23,7 @@ LABEL_ARGMAX, LABEL_GT_FILLED = 0, 1
 NORM_RADIUS, NORM_EUCLID = 0, 1
 UNC_BOXSUM, UNC_PIXEL, UNC_ZERO = 0, 1, 2
 PUR_NORM, PUR_LABEL_HIST, PUR_RADIUS_BINS, PUR_ZERO = 0, 1, 2, 3
+SELECT_KEEP_SCORE = 0x1
 
 ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = -1, -2, -3, -4
 
@@ -41,8 +42,8 @@ _SIGNATURES = {
     "halo_score_workspace_bytes": (_sz, [_i]),
     "halo_score": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "halo_select_workspace_bytes": (_sz, [_i, _i, _i, _i]),
-    "halo_select_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
-    "halo_select_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "halo_select_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "halo_select_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -17,8 +17,10 @@ from .floating_region import FloatingRegionScore
 from .hyperbolic import PoincareEmbedding
 
 
-def select_planes(score, active, selected, active_mask, gt, n_regions, active_radius, mask_radius, want_picks=False):
+def select_planes(score, active, selected, active_mask, gt, n_regions, active_radius, mask_radius, want_picks=False,
+                  keep_score=False):
     """Batched in-place selection on device planes.  score (N,H,W) f32|f64; the rest (N,H,W) uint8.
+    keep_score=True skips writing the -inf suppression windows back into `score` (the acquisition path never reads it).
     Returns (n_picked (N,) int32 device tensor, picks (N,n_regions) int32 | None)."""
     lib = nat.load()
     nat.require_cuda(score, "score")
@@ -38,7 +40,8 @@ def select_planes(score, active, selected, active_mask, gt, n_regions, active_ra
     fn = lib.halo_select_f64 if score.dtype == torch.float64 else lib.halo_select_f32
     with torch.cuda.device(dev):
         rc = fn(nat.ptr(score), nat.ptr(active), nat.ptr(selected), nat.ptr(active_mask), nat.ptr(gt), n_regions,
-                int(active_radius), int(mask_radius), nat.ptr(n_picked), nat.ptr(picks), N, H, W, nat.ptr(ws),
+                int(active_radius), int(mask_radius), nat.SELECT_KEEP_SCORE if keep_score else 0, nat.ptr(n_picked),
+                nat.ptr(picks), N, H, W, nat.ptr(ws),
                 ws.numel(), nat.stream_of(score))
     nat.check(rc, "halo_select")
     return n_picked, picks

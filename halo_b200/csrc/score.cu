@@ -158,6 +158,81 @@ __global__ void __launch_bounds__(SC_THREADS) score_pass_a_kernel(const ScoreArg
   }
 }
 
+// Pass A, fast path for the radius-type purities (impurity := radius plane, count := 1) and small windows: no shared
+// memory, one thread per column walking a strip of rows with the last 2r+1 horizontal sums in registers.
+// ~30 instructions per pixel (the generic halo-tile kernel below is instruction-bound at ~300, profiles/r1_k2_k3.md).
+constexpr int SCF_ROWS = 32;     // rows per thread strip
+constexpr int SCF_THREADS = 256; // columns per block
+template <int R>
+__global__ void __launch_bounds__(SCF_THREADS) score_pass_a_fast_kernel(const ScoreArgs a) {
+  const int n = blockIdx.z;
+  const int x = blockIdx.x * SCF_THREADS + threadIdx.x;
+  const int y0 = blockIdx.y * SCF_ROWS;
+  const size_t plane = (size_t)n * a.H * a.W;
+  const float* pu = a.pixunc + plane;
+  const bool box = (a.unc_mode == HALO_UNC_BOXSUM);
+  unsigned umin = 0xffffffffu, umax = 0u, imin = 0xffffffffu, imax = 0u;
+  __shared__ unsigned s_mm[4];
+  if (threadIdx.x < 4) s_mm[threadIdx.x] = (threadIdx.x & 1) ? 0u : 0xffffffffu;
+  __syncthreads();
+  if (x < a.W) {
+    float ring[2 * R + 1];
+#pragma unroll
+    for (int i = 0; i < 2 * R + 1; ++i) ring[i] = 0.f;
+    auto hsum = [&](int y) -> float {
+      if (y < 0 || y >= a.H || a.unc_mode == HALO_UNC_ZERO) return 0.f;
+      const float* row = pu + (size_t)y * a.W;
+      if (!box) return row[x];
+      float s = 0.f;
+#pragma unroll
+      for (int dx = -R; dx <= R; ++dx) {
+        const int xx = x + dx;
+        if (xx >= 0 && xx < a.W) s += __ldg(row + xx);
+      }
+      return s;
+    };
+    // prime the window with rows y0-R .. y0+R-1
+#pragma unroll
+    for (int i = 0; i < 2 * R; ++i) ring[i + 1] = box ? hsum(y0 - R + i) : 0.f;
+    const int y_end = min(y0 + SCF_ROWS, a.H);
+    for (int y = y0; y < y_end; ++y) {
+#pragma unroll
+      for (int i = 0; i < 2 * R; ++i) ring[i] = ring[i + 1];
+      ring[2 * R] = box ? hsum(y + R) : 0.f;
+      float unc;
+      if (box) {
+        unc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 2 * R + 1; ++i) unc += ring[i];
+      } else {
+        unc = hsum(y);
+      }
+      const size_t g = plane + (size_t)y * a.W + x;
+      const float imp = (a.pur_mode == HALO_PUR_NORM) ? a.radius[g] : 0.f;
+      a.uncertainty[g] = unc;
+      if (a.impurity != nullptr) a.impurity[g] = imp;
+      const unsigned uo = f2ord(unc), io = f2ord(imp);
+      umin = min(umin, uo); umax = max(umax, uo); imin = min(imin, io); imax = max(imax, io);
+    }
+  }
+  if (a.normalize) {
+    for (int o = 16; o > 0; o >>= 1) {
+      umin = min(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+      umax = max(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+      imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o));
+      imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&s_mm[0], umin); atomicMax(&s_mm[1], umax); atomicMin(&s_mm[2], imin); atomicMax(&s_mm[3], imax);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      atomicMin(&a.mm[4 * n + 0], s_mm[0]); atomicMax(&a.mm[4 * n + 1], s_mm[1]);
+      atomicMin(&a.mm[4 * n + 2], s_mm[2]); atomicMax(&a.mm[4 * n + 3], s_mm[3]);
+    }
+  }
+}
+
 // Pass B, 4 pixels per thread (planes are 16-byte aligned and H*W % 4 == 0 in the vector variant).
 // normalize: 0 = off; 1 = on, the two maps are normalised in place (what the reference returns);
 //            2 = on, maps left as pass A wrote them (the acquisition path only needs the score: saves 4-8 B/px)
@@ -265,12 +340,22 @@ extern "C" int halo_score(const float* pixunc, const float* radius, const float*
   }
   const bool hist = (pur_mode == HALO_PUR_LABEL_HIST || pur_mode == HALO_PUR_RADIUS_BINS);
   const int ru = (unc_mode == HALO_UNC_BOXSUM) ? k / 2 : 0, rp = hist ? pk / 2 : 0, r = ru > rp ? ru : rp;
-  const size_t smem = (size_t)(SC_TW + 2 * r) * (SC_TH + 2 * r) * 5 + 16;
-  HALO_CUDA(cudaFuncSetAttribute(score_pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((W + SC_TW - 1) / SC_TW, (H + SC_TH - 1) / SC_TH, N);
-  HALO_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "halo_score: grid too large");
-  score_pass_a_kernel<<<grid, SC_THREADS, smem, st>>>(a);
-  int rc = launch_status("score_pass_a_kernel");
+  int rc;
+  if (!hist && ru <= 2) {
+    dim3 grid((W + SCF_THREADS - 1) / SCF_THREADS, (H + SCF_ROWS - 1) / SCF_ROWS, N);
+    HALO_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "halo_score: grid too large");
+    if (ru == 0) score_pass_a_fast_kernel<0><<<grid, SCF_THREADS, 0, st>>>(a);
+    else if (ru == 1) score_pass_a_fast_kernel<1><<<grid, SCF_THREADS, 0, st>>>(a);
+    else score_pass_a_fast_kernel<2><<<grid, SCF_THREADS, 0, st>>>(a);
+    rc = launch_status("score_pass_a_fast_kernel");
+  } else {
+    const size_t smem = (size_t)(SC_TW + 2 * r) * (SC_TH + 2 * r) * 5 + 16;
+    HALO_CUDA(cudaFuncSetAttribute(score_pass_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((W + SC_TW - 1) / SC_TW, (H + SC_TH - 1) / SC_TH, N);
+    HALO_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535, "halo_score: grid too large");
+    score_pass_a_kernel<<<grid, SC_THREADS, smem, st>>>(a);
+    rc = launch_status("score_pass_a_kernel");
+  }
   if (rc) return rc;
   const long long total = (long long)N * H * W;
   auto aligned = [](const void* q, size_t al) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % al) == 0; };

@@ -72,7 +72,7 @@ def acquire_batch(feat, P, A, cfg, gt, active, selected, active_mask, *, want_sc
         out["score"] = score.clone()
     n_regions = cfg.regions_per_image(H, W)
     n_picked, picks = select_planes(score, active, selected, active_mask, gt, n_regions, cfg.radius_k,
-                                    cfg.mask_radius_k, want_picks=want_picks)
+                                    cfg.mask_radius_k, want_picks=want_picks, keep_score=True)
     out["n_picked"] = n_picked
     out["n_regions"] = n_regions
     if want_picks:

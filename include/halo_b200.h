@@ -135,13 +135,16 @@ int halo_score(const float* pixunc, const float* radius, const float* radius_sta
  * smallest w then smallest h; stop at -inf; score/active window of radius mask_radius := -inf/1;
  * selected window of radius active_radius := 1; active_mask window := gt window }.  In place on all four.
  *   score [N,H,W] f32|f64; active, selected, active_mask, gt [N,H,W] u8
- *   n_picked [N] i32 out; picks [N,n_regions] i32 out|NULL (h*W+w in pick order, -1 padded) */
+ *   n_picked [N] i32 out; picks [N,n_regions] i32 out|NULL (h*W+w in pick order, -1 padded)
+ *   flags: HALO_SELECT_KEEP_SCORE leaves `score` untouched (the caller does not need the -inf windows written back;
+ *          active / selected / active_mask are updated as usual) */
+#define HALO_SELECT_KEEP_SCORE 0x1
 size_t halo_select_workspace_bytes(int N, int H, int W, int n_regions);
 int halo_select_f32(float* score, uint8_t* active, uint8_t* selected, uint8_t* active_mask, const uint8_t* gt,
-                    int n_regions, int active_radius, int mask_radius, int* n_picked, int* picks,
+                    int n_regions, int active_radius, int mask_radius, int flags, int* n_picked, int* picks,
                     int N, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
 int halo_select_f64(double* score, uint8_t* active, uint8_t* selected, uint8_t* active_mask, const uint8_t* gt,
-                    int n_regions, int active_radius, int mask_radius, int* n_picked, int* picks,
+                    int n_regions, int active_radius, int mask_radius, int flags, int* n_picked, int* picks,
                     int N, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
 
 #ifdef __cplusplus

@@ -52,7 +52,7 @@ def test_bad_arguments_return_status_not_crash():
     assert rc == nat.ERR_WORKSPACE
     rc = lib.halo_score(one, one, None, None, None, 0, 0, 1, 4, 3, 19, one, None, one, 1, 8, 8, one, 64, None)
     assert rc == nat.ERR_BAD_ARG and "odd" in nat.last_error()
-    rc = lib.halo_select_f32(one, one, one, one, one, -1, 1, 5, one, None, 1, 8, 8, one, 1 << 20, None)
+    rc = lib.halo_select_f32(one, one, one, one, one, -1, 1, 5, 0, one, None, 1, 8, 8, one, 1 << 20, None)
     assert rc == nat.ERR_BAD_ARG
     with pytest.raises(ValueError):
         nat.check(nat.ERR_BAD_ARG, "x")
