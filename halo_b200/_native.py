@@ -39,6 +39,8 @@ _SIGNATURES = {
     "halo_expmap0_project": (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _vp]),
     "halo_ball_norm": (_i, [_vp, _i, _f, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "halo_logits_stats": (_i, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "halo_upsample_workspace_bytes": (_sz, [_i, _i, _i]),
+    "halo_upsample_score_inputs": (_i, [_vp, _vp, _i, _f, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "halo_score_workspace_bytes": (_sz, [_i]),
     "halo_score": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "halo_select_workspace_bytes": (_sz, [_i, _i, _i, _i]),

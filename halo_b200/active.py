@@ -120,18 +120,19 @@ def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_
                 active = active_indicator[i]
                 selected = selected_indicator[i]
 
-                output = F.interpolate(tgt_out[i:i + 1], size=size, mode="bilinear", align_corners=True)
-                emb = None
-                if needs_embedding:
-                    emb = decoder_out[i:i + 1]
-                    same = tuple(emb.shape[-2:]) == size
-                    if not (isinstance(emb, PoincareEmbedding) and same):
-                        # reference build.py:132-135: the embedding itself is up-sampled, THEN measured
-                        emb = F.interpolate(emb, size=size, mode="bilinear", align_corners=True)
-
-                score, _, _ = floating_region_score(output, decoder_out=emb, normalize=cfg.ACTIVE.NORMALIZE,
-                                                    unc_type=uncertainty_type, pur_type=purity_type,
-                                                    ground_truth=ground_truth)
+                out_i = tgt_out[i:i + 1]
+                emb = decoder_out[i:i + 1] if needs_embedding else None
+                if tuple(out_i.shape[-2:]) == size and (emb is None or tuple(emb.shape[-2:]) == size):
+                    # already at label size (reference: F.interpolate to the same size is the identity)
+                    score, _, _ = floating_region_score(out_i, decoder_out=emb, normalize=cfg.ACTIVE.NORMALIZE,
+                                                        unc_type=uncertainty_type, pur_type=purity_type,
+                                                        ground_truth=ground_truth)
+                else:
+                    # reference build.py:122-135 up-samples logits and (fp64) embedding -- possibly from different
+                    # resolutions (classifier.py:556-557) -- THEN scores; fused here, nothing is materialised
+                    score, _, _ = floating_region_score.forward_upsampled(
+                        out_i, emb, size, normalize=cfg.ACTIVE.NORMALIZE, unc_type=uncertainty_type,
+                        pur_type=purity_type, ground_truth=ground_truth)
                 score[active.to(score.device)] = -float("inf")
                 active_regions = math.ceil(size[0] * size[1] * active_budget / per_region_pixels)
                 score, active, selected, active_mask = select_pixels_to_label(

@@ -166,3 +166,74 @@ class FloatingRegionScore(nn.Module):
         if N == 1:
             return score[0], imp[0], unc[0]
         return score, imp, unc
+
+    def forward_upsampled(self, logit_lr, decoder_out_lr, size, unc_type=None, pur_type=None, normalize=False,
+                          ground_truth=None):
+        """Score at label resolution from LOW-resolution logits and embedding (extension).
+
+        Equivalent to the reference sequence of `RegionSelection` (core/active/build.py:122-144):
+            output = F.interpolate(logit_lr, size, mode="bilinear", align_corners=True)
+            decoder_out = F.interpolate(decoder_out_lr, size, mode="bilinear", align_corners=True)
+            floating_region_score(output, decoder_out=decoder_out, ...)
+        but the two up-sampled tensors (O and C channels at label size, the latter float64 in the reference) are never
+        materialised: `halo_upsample_score_inputs` interpolates per output pixel and writes the three planes K2 needs.
+        decoder_out_lr: PoincareEmbedding (raw features, exp-map applied at the low-resolution pixels) or a tensor of
+        ball points (fp32/fp64), or None."""
+        lib = nat.load()
+        nat.require_cuda(logit_lr, "logit")
+        unc_mode, pixunc_mode, pur_mode, label_mode, norm_mode = modes_for(unc_type, pur_type)
+        if pur_type in ("ripu", "oracle_ripu") and self.purity_type == "hyper":
+            raise RuntimeError("FloatingRegionScore built for 'hyper' purity cannot score '%s'" % pur_type)
+        logit_lr = logit_lr.float().contiguous()
+        N, O, h, w = logit_lr.shape
+        H, W = int(size[0]), int(size[1])
+        dev = logit_lr.device
+        gt8 = None
+        if pixunc_mode == "one_minus_pgt" or label_mode == "gt_filled":
+            if ground_truth is None:
+                raise ValueError("ground_truth is required by unc_type/pur_type '%s'/'%s'" % (unc_type, pur_type))
+            gt8 = nat.require_cuda(ground_truth, "ground_truth").to(torch.uint8).reshape(N, H, W).contiguous()
+        need_pixunc = unc_mode != nat.UNC_ZERO
+        need_label = pur_mode == nat.PUR_LABEL_HIST
+        need_radius = pur_mode in (nat.PUR_NORM, nat.PUR_RADIUS_BINS)
+        pixunc = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need_pixunc else None
+        label = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if need_label else None
+        radius = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need_radius else None
+        stats = torch.empty((N, 4), dtype=torch.float32, device=dev) if pur_mode == nat.PUR_RADIUS_BINS else None
+        emb, emb_kind, C = None, nat.FEAT_BALL_F32, 0
+        if need_radius:
+            if decoder_out_lr is None:
+                raise ValueError("decoder_out is required by pur_type '%s'" % pur_type)
+            if isinstance(decoder_out_lr, PoincareEmbedding):
+                emb, emb_kind = decoder_out_lr.u.detach().float().contiguous(), nat.FEAT_TANGENT_F32
+            else:
+                emb = nat.require_cuda(decoder_out_lr, "decoder_out")
+                if emb.dtype == torch.float64:
+                    emb_kind = nat.FEAT_BALL_F64
+                else:
+                    emb, emb_kind = emb.float(), nat.FEAT_BALL_F32
+                emb = emb.contiguous()
+            if emb.shape[0] != N:
+                raise ValueError("logits and embedding must share the batch size")
+            C = emb.shape[1]
+        eh, ew = (int(emb.shape[-2]), int(emb.shape[-1])) if emb is not None else (h, w)
+        ws = nat.workspace.get(dev, "upsample", lib.halo_upsample_workspace_bytes(N, eh, ew))
+        with torch.cuda.device(dev):
+            rc = lib.halo_upsample_score_inputs(
+                nat.ptr(logit_lr) if (need_pixunc or need_label) else None, nat.ptr(emb), emb_kind, float(self.mapper.c),
+                nat.ptr(gt8), nat.PIXUNC_ONE_MINUS_PGT if pixunc_mode == "one_minus_pgt" else nat.PIXUNC_ENTROPY,
+                nat.LABEL_GT_FILLED if label_mode == "gt_filled" else nat.LABEL_ARGMAX,
+                nat.NORM_EUCLID if norm_mode == "euclid" else nat.NORM_RADIUS, nat.ptr(pixunc), nat.ptr(label),
+                nat.ptr(radius), nat.ptr(stats), N, O, C, h, w, eh, ew, H, W, nat.ptr(ws), ws.numel(),
+                nat.stream_of(logit_lr))
+        nat.check(rc, "halo_upsample_score_inputs")
+        n_bins = self.K if pur_mode == nat.PUR_RADIUS_BINS else self.in_channels
+        if pixunc is None and radius is None:
+            pixunc = torch.zeros((N, H, W), dtype=torch.float32, device=dev)
+        score, imp, unc = score_planes(pixunc, radius, stats, label, None, unc_mode=unc_mode, pur_mode=pur_mode,
+                                       normalize=normalize, k=self.size, pk=self.purity_size, n_bins=n_bins,
+                                       want_impurity=True)
+        if N == 1:
+            return score[0], imp[0], unc[0]
+        return score, imp, unc
+

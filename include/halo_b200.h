@@ -116,6 +116,20 @@ int halo_ball_norm(const void* x, int x_f64, float c, int norm_mode, float* out,
 int halo_logits_stats(const float* logits, const uint8_t* gt, int pixunc_mode, int label_mode,
                       float* pixunc, uint8_t* label, int N, int O, int H, int W, halo_stream_t stream);
 
+/* ---- fused bilinear up-sampling in front of the score (core/active/build.py:122-135) ------------------
+ * Replaces F.interpolate(logits, size, bilinear, align_corners=True) (:123-125) followed by softmax entropy / argmax
+ * (floating_region.py:152,166) and F.interpolate(decoder_out, ...) (:132-135) followed by poincare_distance_origin /
+ * norm (floating_region.py:188,195), per OUTPUT pixel, without materialising either up-sampled tensor.
+ *   logits_lr [N,O,lh,lw] f32 | NULL;  emb_lr [N,C,eh,ew] per emb_kind (halo_feat_kind: raw features get
+ *   expmap0+project at the low-resolution pixels first) | NULL -- the two may come at different resolutions (the
+ *   DeepLab v3+ head up-samples only its logits, classifier.py:556-557);  outputs at [N,H,W]: pixunc f32, label u8,
+ *   radius f32, stats [N,4].  ws: halo_upsample_workspace_bytes(N,eh,ew) (only read for HALO_FEAT_TANGENT_F32). */
+size_t halo_upsample_workspace_bytes(int N, int h, int w);
+int halo_upsample_score_inputs(const float* logits_lr, const void* emb_lr, int emb_kind, float c, const uint8_t* gt,
+                               int pixunc_mode, int label_mode, int norm_mode, float* pixunc, uint8_t* label,
+                               float* radius, float* stats, int N, int O, int C, int lh, int lw, int eh, int ew,
+                               int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
+
 /* ---- floating-region score (core/active/floating_region.py:129-217 after the softmax) ---------------
  *   pixunc [N,H,W] f32, radius [N,H,W] f32 (+ its stats [N,4]), label [N,H,W] u8, active [N,H,W] u8|NULL
  *   k = uncertainty window (odd), pk = purity window (odd; 3 when the module was built for "hyper"),

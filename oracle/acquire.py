@@ -45,3 +45,14 @@ def acquire_image(
                                                       active_mask, ground_truth)
     return dict(score=score_before, score_after=score, active=active, selected=selected, active_mask=active_mask,
                 picks=picks, logits=logits, radius=rad[0], impurity=imp, uncertainty=unc, n_regions=n_regions)
+
+
+def upsampled_score(logits_lr, x_lr, out_size, **score_kwargs):
+    """build.py:122-144: bilinear (align_corners=True) up-sampling of the logits and of the (fp64) embedding to the
+    label size, then FloatingRegionScore on the up-sampled tensors."""
+    import torch.nn.functional as F
+
+    out = F.interpolate(logits_lr, size=out_size, mode="bilinear", align_corners=True)
+    emb = F.interpolate(x_lr, size=out_size, mode="bilinear", align_corners=True) if x_lr is not None else None
+    return _score.floating_region_score(out, decoder_out=emb, **score_kwargs)
+
