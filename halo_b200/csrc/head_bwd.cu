@@ -17,8 +17,8 @@ namespace halo {
 constexpr int BWD_THREADS = 256;
 constexpr int BWD_PIX = 2;
 constexpr int BWD_U = 4;
-constexpr int DW_THREADS = 128;   // each thread owns 2 channels of a 256-channel block
-constexpr int DW_PX = 32;         // pixels per shared-memory sub-tile
+constexpr int DW_THREADS = 256;   // thread t owns channel t of a 256-channel block
+constexpr int DW_PX = 32;         // pixels per unit (shared-memory strip)
 
 struct BwdArgs {
   const float* feat;
@@ -220,41 +220,59 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) head_bwd_pix_kernel(const BwdA
       }
     }
     // ---- pass 2: du = alpha*u + [gS gT] . Wt^T ----
+    // Channels are independent here: process BWD_U of them per trip (loads issued first) and split every dot product
+    // over 4 partial sums, so the FMA chains are 10 deep instead of 40 (the single-chain version was latency-bound).
     float* dbase = a.dfeat + (size_t)n * a.C * HW;
-    for (int ch = 0; ch < a.C; ++ch) {
-      float u[BWD_PIX] = {0.f, 0.f};
-      if (VEC) {
-        if (p < HW) {
-          const float2 t = __ldg(reinterpret_cast<const float2*>(base + (size_t)ch * HW + p));
-          u[0] = t.x;
-          u[1] = t.y;
+    for (int cb = 0; cb < a.C; cb += BWD_U) {
+      float u[BWD_U][BWD_PIX];
+#pragma unroll
+      for (int j = 0; j < BWD_U; ++j) {
+        const int ch = cb + j;
+        u[j][0] = u[j][1] = 0.f;
+        if (ch < a.C) {
+          if (VEC) {
+            if (p < HW) {
+              const float2 t = __ldg(reinterpret_cast<const float2*>(base + (size_t)ch * HW + p));
+              u[j][0] = t.x;
+              u[j][1] = t.y;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < BWD_PIX; ++i)
+              if (p + i < HW) u[j][i] = __ldg(base + (size_t)ch * HW + p + i);
+          }
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < BWD_PIX; ++i)
-          if (p + i < HW) u[i] = __ldg(base + (size_t)ch * HW + p + i);
       }
-      float d[BWD_PIX];
 #pragma unroll
-      for (int i = 0; i < BWD_PIX; ++i) d[i] = alpha[i] * u[i];
-      const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)ch * KP);
-#pragma unroll
-      for (int q = 0; q < KP / 4; ++q) {
-        const float4 w = w4[q];
+      for (int j = 0; j < BWD_U; ++j) {
+        const int ch = cb + j;
+        if (ch >= a.C) break;
+        float d[BWD_PIX][4];
 #pragma unroll
         for (int i = 0; i < BWD_PIX; ++i) {
-          d[i] = fmaf(acc[i][4 * q + 0], w.x, d[i]);
-          d[i] = fmaf(acc[i][4 * q + 1], w.y, d[i]);
-          d[i] = fmaf(acc[i][4 * q + 2], w.z, d[i]);
-          d[i] = fmaf(acc[i][4 * q + 3], w.w, d[i]);
+          d[i][0] = alpha[i] * u[j][i];
+          d[i][1] = d[i][2] = d[i][3] = 0.f;
         }
-      }
-      if (VEC) {
-        if (p < HW) __stcs(reinterpret_cast<float2*>(dbase + (size_t)ch * HW + p), make_float2(d[0], d[1]));
-      } else {
+        const float4* w4 = reinterpret_cast<const float4*>(sW + (size_t)ch * KP);
 #pragma unroll
-        for (int i = 0; i < BWD_PIX; ++i)
-          if (p + i < HW) dbase[(size_t)ch * HW + p + i] = d[i];
+        for (int q = 0; q < KP / 4; ++q) {
+          const float4 w = w4[q];
+#pragma unroll
+          for (int i = 0; i < BWD_PIX; ++i) {
+            d[i][0] = fmaf(acc[i][4 * q + 0], w.x, d[i][0]);
+            d[i][1] = fmaf(acc[i][4 * q + 1], w.y, d[i][1]);
+            d[i][2] = fmaf(acc[i][4 * q + 2], w.z, d[i][2]);
+            d[i][3] = fmaf(acc[i][4 * q + 3], w.w, d[i][3]);
+          }
+        }
+        const float d0 = (d[0][0] + d[0][1]) + (d[0][2] + d[0][3]);
+        const float d1 = (d[1][0] + d[1][1]) + (d[1][2] + d[1][3]);
+        if (VEC) {
+          if (p < HW) __stcs(reinterpret_cast<float2*>(dbase + (size_t)ch * HW + p), make_float2(d0, d1));
+        } else {
+          if (p < HW) dbase[(size_t)ch * HW + p] = d0;
+          if (p + 1 < HW) dbase[(size_t)ch * HW + p + 1] = d1;
+        }
       }
     }
   }
@@ -267,61 +285,74 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) head_bwd_pix_kernel(const BwdA
 }
 
 // K4b: dW[k][c] = sum_pix G[k][pix] * u[c][pix].  Persistent CTAs, register accumulators, one partial per CTA.
+// 256 threads: thread t owns channel c0+t and all 2*OP rows; the u/G strips of the NEXT unit are fetched into
+// registers while the FMAs of the current unit run out of shared memory (software pipelining across units).
 template <int OP>
 __global__ void __launch_bounds__(DW_THREADS) head_bwd_dw_kernel(const float* __restrict__ feat, const float* __restrict__ G,
                                                                   float* __restrict__ dw_part, int N, int C, int HW,
                                                                   int cblocks, long long total_units) {
   constexpr int KP = 2 * OP;
+  constexpr int UPT = 256 * DW_PX / DW_THREADS;          // u elements fetched per thread per unit
+  constexpr int GPT = (KP * DW_PX + DW_THREADS - 1) / DW_THREADS;
   __shared__ float sU[256][DW_PX + 1];
   __shared__ __align__(16) float sG[DW_PX][KP];
-  const int tid = threadIdx.x;
-  // a "unit" = (channel block of 256, image, 32-pixel strip); units of one channel block are contiguous per CTA
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int strips = (HW + DW_PX - 1) / DW_PX;
   for (int cbk = 0; cbk < cblocks; ++cbk) {
-    float acc[2][KP];
+    float acc[KP];
 #pragma unroll
-    for (int k = 0; k < KP; ++k) acc[0][k] = acc[1][k] = 0.f;
+    for (int k = 0; k < KP; ++k) acc[k] = 0.f;
     const int c0 = cbk * 256;
-    for (long long unit = blockIdx.x; unit < (long long)N * strips; unit += gridDim.x) {
+    float ru[UPT], rg[GPT];
+    auto fetch = [&](long long unit) {
       const int n = (int)(unit / strips);
       const int p0 = (int)(unit - (long long)n * strips) * DW_PX;
-      __syncthreads();
-      // u tile: warp w loads channels w, w+4, ... ; lane = pixel (coalesced 128 B rows)
-      for (int r = tid >> 5; r < 256; r += DW_THREADS / 32) {
-        const int ch = c0 + r, px = p0 + (tid & 31);
-        sU[r][tid & 31] = (ch < C && px < HW) ? __ldg(feat + ((size_t)n * C + ch) * HW + px) : 0.f;
+#pragma unroll
+      for (int e = 0; e < UPT; ++e) {
+        const int r = wrp + e * (DW_THREADS / 32);       // channel row within the block; lane = pixel
+        const int ch = c0 + r, px = p0 + lane;
+        ru[e] = (ch < C && px < HW) ? __ldg(feat + ((size_t)n * C + ch) * HW + px) : 0.f;
       }
-      for (int i = tid; i < DW_PX * KP; i += DW_THREADS) {
+#pragma unroll
+      for (int e = 0; e < GPT; ++e) {
+        const int i = tid + e * DW_THREADS;
         const int k = i / DW_PX, j = i - k * DW_PX;
         const int px = p0 + j;
-        sG[j][k] = (px < HW) ? __ldg(G + ((size_t)n * KP + k) * HW + px) : 0.f;
+        rg[e] = (i < KP * DW_PX && px < HW) ? __ldg(G + ((size_t)n * KP + k) * HW + px) : 0.f;
+      }
+    };
+    long long unit = blockIdx.x;
+    if (unit < total_units) fetch(unit);
+    for (; unit < total_units; unit += gridDim.x) {
+      __syncthreads();                                   // previous unit's FMAs are done with sU / sG
+#pragma unroll
+      for (int e = 0; e < UPT; ++e) sU[wrp + e * (DW_THREADS / 32)][lane] = ru[e];
+#pragma unroll
+      for (int e = 0; e < GPT; ++e) {
+        const int i = tid + e * DW_THREADS;
+        if (i < KP * DW_PX) sG[i % DW_PX][i / DW_PX] = rg[e];
       }
       __syncthreads();
+      if (unit + gridDim.x < total_units) fetch(unit + gridDim.x);   // in flight during the FMAs below
 #pragma unroll 4
       for (int j = 0; j < DW_PX; ++j) {
-        const float u0 = sU[tid][j], u1 = sU[tid + 128][j];
+        const float u0 = sU[tid][j];
         const float4* g4 = reinterpret_cast<const float4*>(&sG[j][0]);
 #pragma unroll
         for (int q = 0; q < KP / 4; ++q) {
           const float4 g = g4[q];
-          acc[0][4 * q + 0] = fmaf(g.x, u0, acc[0][4 * q + 0]);
-          acc[0][4 * q + 1] = fmaf(g.y, u0, acc[0][4 * q + 1]);
-          acc[0][4 * q + 2] = fmaf(g.z, u0, acc[0][4 * q + 2]);
-          acc[0][4 * q + 3] = fmaf(g.w, u0, acc[0][4 * q + 3]);
-          acc[1][4 * q + 0] = fmaf(g.x, u1, acc[1][4 * q + 0]);
-          acc[1][4 * q + 1] = fmaf(g.y, u1, acc[1][4 * q + 1]);
-          acc[1][4 * q + 2] = fmaf(g.z, u1, acc[1][4 * q + 2]);
-          acc[1][4 * q + 3] = fmaf(g.w, u1, acc[1][4 * q + 3]);
+          acc[4 * q + 0] = fmaf(g.x, u0, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(g.y, u0, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(g.z, u0, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(g.w, u0, acc[4 * q + 3]);
         }
       }
     }
     // partial [grid][KP][CP] with CP = cblocks*256
     float* out = dw_part + (size_t)blockIdx.x * KP * (cblocks * 256);
 #pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      out[(size_t)k * (cblocks * 256) + c0 + tid] = acc[0][k];
-      out[(size_t)k * (cblocks * 256) + c0 + tid + 128] = acc[1][k];
-    }
+    for (int k = 0; k < KP; ++k) out[(size_t)k * (cblocks * 256) + c0 + tid] = acc[k];
+    __syncthreads();
   }
 }
 
@@ -403,7 +434,7 @@ static int bwd_grids(int N, int HW, int* pix_grid, int* dw_grid) {
   if (g > tiles) g = tiles;
   *pix_grid = g;
   const long long units = (long long)N * ((HW + DW_PX - 1) / DW_PX);
-  long long d = (long long)sm_count() * 4;
+  long long d = (long long)sm_count() * 3;
   if (d > units) d = units;
   *dw_grid = (int)d;
   return 0;
