@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) head_bwd_pix_kernel(const BwdA
 // 256 threads: thread t owns channel c0+t and all 2*OP rows; the u/G strips of the NEXT unit are fetched into
 // registers while the FMAs of the current unit run out of shared memory (software pipelining across units).
 template <int OP>
-__global__ void __launch_bounds__(DW_THREADS) head_bwd_dw_kernel(const float* __restrict__ feat, const float* __restrict__ G,
+__global__ void __launch_bounds__(DW_THREADS, 2) head_bwd_dw_kernel(const float* __restrict__ feat, const float* __restrict__ G,
                                                                   float* __restrict__ dw_part, int N, int C, int HW,
                                                                   int cblocks, long long total_units) {
   constexpr int KP = 2 * OP;

@@ -85,16 +85,21 @@ def test_second_round_respects_existing_labels():
         assert (d["active"][i] >= act1[i]).all() and (d["selected"][i] >= sel1[i]).all()
 
 
-def test_full_size_properties():
-    """BASELINE config-2 image size: properties that do not need the oracle."""
-    C, O, H, W = 256, 19, 640, 1280
-    cfg = halo_b200.AcquisitionConfig(budget=0.05)
+@pytest.mark.parametrize("name,cfg,O,expect", [
+    ("cfg2_gtav_cityscapes", halo_b200.AcquisitionConfig(budget=0.05), 19, 4552),
+    ("cfg2_reference_default_round", halo_b200.AcquisitionConfig(budget=0.05, n_rounds=5), 19, 911),
+    ("cfg4_synthia_5x5", halo_b200.AcquisitionConfig(num_classes=16, radius_k=2, budget=0.022), 16, 721),
+])
+def test_full_size_properties(name, cfg, O, expect):
+    """BASELINE config-2 / config-4 image size: properties that do not need the oracle."""
+    C, H, W = 256, 640, 1280
     P, A = synth.head_params(O, C, seed=0)
     d = synth.batch(0, 2, C, O, H, W, device=DEV)
     res = halo_b200.acquire_batch(d["feat"], P.to(DEV), A.to(DEV), cfg, d["gt"], d["active"], d["selected"],
                                   d["active_mask"], want_picks=True)
     n_regions = cfg.regions_per_image(H, W)
-    assert n_regions == 4552
+    assert n_regions == expect
+    ar, mr = cfg.radius_k, cfg.mask_radius_k
     for i in range(2):
         k = int(res["n_picked"][i])
         assert k == n_regions
@@ -104,15 +109,38 @@ def test_full_size_properties():
         # no two picks within the suppression radius: dilating picks by m never covers another pick
         grid = torch.zeros((H, W), dtype=torch.int32, device=DEV)
         grid[hh, ww] = 1
-        cnt = torch.nn.functional.conv2d(grid[None, None].float(), torch.ones(1, 1, 11, 11, device=DEV), padding=5)[0, 0]
+        cnt = torch.nn.functional.conv2d(grid[None, None].float(), torch.ones(1, 1, 2 * mr + 1, 2 * mr + 1, device=DEV),
+                                         padding=mr)[0, 0]
         assert int(cnt[hh, ww].max()) == 1
         sel = d["selected"][i].bool()
         assert torch.equal(d["active_mask"][i][sel], d["gt"][i][sel])
         assert (d["active_mask"][i][~sel] == 255).all()
-        assert sel.sum().item() <= 9 * k and d["active"][i].sum().item() <= 121 * k
-        assert (d["active"][i].bool() | ~sel).all()        # selected implies active
+        assert sel.sum().item() <= (2 * ar + 1) ** 2 * k and d["active"][i].sum().item() <= (2 * max(mr, 0) + 1) ** 2 * k
+        if mr >= ar:
+            assert (d["active"][i].bool() | ~sel).all()    # selected implies active
     # idempotence of a zero budget
     before = d["active_mask"].clone()
     zero = halo_b200.AcquisitionConfig(budget=0.0)
     r0 = halo_b200.acquire_batch(d["feat"], P.to(DEV), A.to(DEV), zero, d["gt"], d["active"], d["selected"], d["active_mask"])
     assert r0["n_picked"].sum().item() == 0 and torch.equal(before, d["active_mask"])
+
+
+def test_runs_on_a_side_stream_and_accepts_strided_inputs():
+    """Every entry point enqueues on the caller's current stream; non-contiguous features are made contiguous."""
+    C, O, H, W = 64, 19, 64, 96
+    cfg = halo_b200.AcquisitionConfig(budget=0.022)
+    P, A = synth.head_params(O, C, seed=0)
+    b = synth.batch(0, 2, C, O, H, W)
+    d = {k: v.to(DEV) for k, v in b.items()}
+    ref = halo_b200.acquire_batch(d["feat"], P.to(DEV), A.to(DEV), cfg, d["gt"], d["active"].clone(), d["selected"].clone(),
+                                  d["active_mask"].clone(), want_score=True)
+    side = torch.cuda.Stream()
+    feat_cl = d["feat"].to(memory_format=torch.channels_last)          # NHWC strides: must not be mis-read as NCHW
+    assert not feat_cl.is_contiguous()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        out = halo_b200.acquire_batch(feat_cl, P.to(DEV), A.to(DEV), cfg, d["gt"], d["active"], d["selected"],
+                                      d["active_mask"], want_score=True)
+    side.synchronize()
+    assert torch.equal(out["score"], ref["score"]) and torch.equal(out["n_picked"], ref["n_picked"])
+
