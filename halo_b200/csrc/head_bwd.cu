@@ -9,8 +9,11 @@
 //     dP, dA from dW and the per-class scalars d/dpp, d/dan, d/dpa by the chain rule             (K4c)
 // Reductions over pixels are two-stage with a fixed order (per-CTA partials, then one finalize block per
 // class), so gradients are bitwise reproducible for a given grid size.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "head_common.cuh"
+#include "head_tc.cuh"
 
 namespace halo {
 
@@ -112,84 +115,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) head_bwd_pix_kernel(const BwdA
 #pragma unroll
     for (int i = 0; i < BWD_PIX; ++i) {
       const bool live = (p + i < HW);
-      const float nn = sqrtf(n2[i]);
-      const float nsafe = fmaxf(nn, 1e-15f);
-      const float sn = hc.s * nn;
-      const bool clipped = sn > hc.z_clip;
-      const float z = fminf(sn, hc.z_clip);
-      const float e = expf(-2.f * z);
-      const float t = clipped ? hc.t_clip : tanhf(z);
-      const float ope = 1.f + e;
-      const float omega = clipped ? hc.omega_clip : 4.f * e / (ope * ope);
-      const float gamma = t / (hc.s * nsafe);
-      const float t2 = t * t;
-      // derivatives of the per-pixel scalars w.r.t. n2
-      float dgam, dt2, dom;
-      if (clipped) {
-        dgam = -gamma / (2.f * fmaxf(n2[i], 1e-30f));
-        dt2 = 0.f;
-        dom = 0.f;
-      } else {
-        dgam = (z < 1e-3f) ? (-hc.c * (1.f / 3.f)) : (omega - gamma) / (2.f * fmaxf(n2[i], 1e-30f));
-        dt2 = t * hc.s * omega / nsafe;
-        dom = -t * omega * hc.s / nsafe;
-        if (nn < 1e-15f) { dt2 = hc.c; dom = -hc.c; }  // limits at the origin
-      }
+      const PixelScalarGrads ps = tangent_scalar_grads(n2[i], hc);
       float g_gamma = 0.f, g_t2 = 0.f, g_om = 0.f;
 #pragma unroll
       for (int k = 0; k < OP; ++k) {
         float gS = 0.f, gT = 0.f;
         if (k < a.O) {
           const float G = live ? __ldg(a.dlogits + ((size_t)n * a.O + k) * HW + p + i) : 0.f;
-          const float S = acc[i][k], T = acc[i][OP + k];
-          const float pp = sCls[k], an = sCls[OP + k], pa = sCls[2 * OP + k], Bk = sCls[3 * OP + k];
-          const float px = gamma * S, xa = gamma * T;
-          const float cpx2 = 2.f * hc.c * px;
-          const float Anum = 1.f + cpx2 + t2;
-          const float Draw = 1.f + cpx2 + hc.c * t2 * pp;
-          const bool dclamp = Draw < 1e-12f;
-          const float D = dclamp ? 1e-12f : Draw;
-          const float num = Bk * xa + Anum * pa;
-          const float bo = Bk * omega;
-          const float omc = bo / D;
-          float arg, a_num, a_bo, a_D;
-          if (omc >= hc.om_max) {
-            const float den = fmaxf(bo, 1e-12f * D);
-            arg = hc.two_s * num / den;
-            a_num = hc.two_s / den;
-            a_bo = -arg / den;
-            a_D = 0.f;
-          } else {
-            const float m = fmaxf(1.f - omc, 0.f) * (1.f / hc.c);
-            const float root = fmaxf(sqrtf(m), 1e-12f);
-            const float invD = 1.f / D;
-            arg = num * invD * (hc.out_scale / root);
-            a_num = invD * (hc.out_scale / root);
-            const float a_m = -arg / (2.f * root * root);   // d arg / d m  (through 1/root)
-            a_bo = a_m * (-invD / hc.c);
-            a_D = -arg * invD + a_m * (omc * invD / hc.c);
-          }
-          const float ash = asinhf(arg);
-          const float g = G * hc.two_over_s * an * rsqrtf(1.f + arg * arg);
-          const float g_num = g * a_num, g_bo = g * a_bo, g_D = dclamp ? 0.f : g * a_D;
-          float g_Bk = g_num * xa + g_bo * omega;
-          const float g_xa = g_num * Bk;
-          const float g_Anum = g_num * pa;
-          const float g_cpx2 = g_Anum + g_D;
-          g_t2 += g_Anum + g_D * hc.c * pp;
-          g_om += g_bo * Bk;
-          const float g_px = 2.f * hc.c * g_cpx2;
-          g_gamma += g_px * S + g_xa * T;
-          gS = g_px * gamma;
-          gT = g_xa * gamma;
-          cpp[k] += g_D * hc.c * t2 - hc.c * g_Bk;
-          can[k] += G * hc.two_over_s * ash;
-          cpa[k] += g_num * Anum;
+          mlr_logit_grad(G, acc[i][k], acc[i][OP + k], ps, sCls[k], sCls[OP + k], sCls[2 * OP + k], sCls[3 * OP + k], hc,
+                         gS, gT, g_gamma, g_t2, g_om, cpp[k], can[k], cpa[k]);
         }
         acc[i][k] = gS;
         acc[i][OP + k] = gT;
       }
-      alpha[i] = 2.f * (g_gamma * dgam + g_t2 * dt2 + g_om * dom);
+      alpha[i] = 2.f * (g_gamma * ps.dgam + g_t2 * ps.dt2 + g_om * ps.dom);
     }
     // per-class scalars: fixed-order warp reduction, then this warp's shared-memory slot
 #pragma unroll
@@ -449,9 +388,14 @@ extern "C" size_t halo_head_bwd_workspace_bytes(int N, int C, int O, int H, int 
   b = (b + 255) / 256 * 256;
   b += (size_t)N * KP * H * W * 4;                       // G planes
   b = (b + 255) / 256 * 256;
-  b += (size_t)pg * 3 * OP * 4;                          // class-scalar partials
+  (void)pg;
+  b += (size_t)sm_count() * 2 * 3 * OP * 4;              // class-scalar partials (one slot per CTA of either pixel pass)
   b = (b + 255) / 256 * 256;
   b += (size_t)dg * KP * CP * 4;                         // dW partials
+  b = (b + 255) / 256 * 256;
+  b += head_tc_pack_floats(O, C) * 4;                    // tensor-core parameter planes (MMA1)
+  b = (b + 255) / 256 * 256;
+  b += head_tc_pack_floats(O, C) * 4;                    // transposed planes (MMA2)
   return b + 256;
 }
 
@@ -496,8 +440,12 @@ extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, 
   float* G = (float*)(w8 + off);
   off += (size_t)N * KP * HW * 4; off = (off + 255) / 256 * 256;
   float* cls_part = (float*)(w8 + off);
-  off += (size_t)pix_grid * 3 * OP * 4; off = (off + 255) / 256 * 256;
+  off += (size_t)sm_count() * 2 * 3 * OP * 4; off = (off + 255) / 256 * 256;
   float* dw_part = (float*)(w8 + off);
+  off += (size_t)dw_grid * KP * CP * 4; off = (off + 255) / 256 * 256;
+  float* wtc = (float*)(w8 + off);
+  off += head_tc_pack_floats(O, C) * 4; off = (off + 255) / 256 * 256;
+  float* w2 = (float*)(w8 + off);
 
   cudaStream_t st = (cudaStream_t)stream;
   head_pack_kernel<<<OP, 128, 0, st>>>(P, A, c, O, OP, C, CPAD, wpack, nullptr, 0);
@@ -516,17 +464,37 @@ extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, 
   a.hc = make_head_consts(c);
   const bool vec = (HW % 2 == 0) && ((uintptr_t)feat % 8 == 0) && ((uintptr_t)dfeat % 8 == 0);
   const int cblocks = CP / 256;
-  switch (OP) {
-    case 4: rc = launch_bwd<4>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
-    case 8: rc = launch_bwd<8>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
-    case 12: rc = launch_bwd<12>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
-    case 16: rc = launch_bwd<16>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
-    case 20: rc = launch_bwd<20>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
-    case 24: rc = launch_bwd<24>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
-    case 28: rc = launch_bwd<28>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
-    default: rc = launch_bwd<32>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+  int cls_grid = pix_grid;
+  const char* force_cc = getenv("HALO_BWD_CUDA_CORE");  // parity tests pin the fp32 CUDA-core pixel pass
+  if (!(force_cc && force_cc[0] == '1') && head_bwd_tc_supported(C, O, H, W, feat, dfeat)) {
+    // pixel pass on the tensor cores (head_bwd_tc.cu); the weight-gradient GEMM below is shared
+    rc = head_pack_tc_launch(wpack, wtc, C, CPAD, O, st);
+    if (rc) return rc;
+    cls_grid = head_bwd_tc_grid(N, HW);
+    rc = head_bwd_tc_launch(feat, dlogits, dfeat, G, cls_part, wpack, wtc, w2, c, N, C, O, H, W, cls_grid, st);
+    if (rc) return rc;
+    switch (OP) {
+      case 4: head_bwd_dw_kernel<4><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
+      case 8: head_bwd_dw_kernel<8><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
+      case 12: head_bwd_dw_kernel<12><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
+      case 16: head_bwd_dw_kernel<16><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
+      case 20: head_bwd_dw_kernel<20><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
+      default: head_bwd_dw_kernel<24><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
+    }
+    rc = launch_status("head_bwd_dw_kernel");
+  } else {
+    switch (OP) {
+      case 4: rc = launch_bwd<4>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+      case 8: rc = launch_bwd<8>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+      case 12: rc = launch_bwd<12>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+      case 16: rc = launch_bwd<16>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+      case 20: rc = launch_bwd<20>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+      case 24: rc = launch_bwd<24>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+      case 28: rc = launch_bwd<28>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+      default: rc = launch_bwd<32>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
+    }
   }
   if (rc) return rc;
-  head_bwd_finalize_kernel<<<O, 256, 0, st>>>(P, A, dw_part, dw_grid, cls_part, pix_grid, dP, dA, O, OP, C, CP);
+  head_bwd_finalize_kernel<<<O, 256, 0, st>>>(P, A, dw_part, dw_grid, cls_part, cls_grid, dP, dA, O, OP, C, CP);
   return launch_status("head_bwd_finalize_kernel");
 }

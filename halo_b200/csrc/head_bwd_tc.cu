@@ -1,0 +1,474 @@
+// K4a-TC -- pixel pass of the fused head backward on the Blackwell tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+//   du[px][c] = alpha[px] * u[px][c] + sum_n G[px][n] * W[n][c]      G = [gS | gT] (analytic epilogue derivative)
+//
+// Two chained GEMMs per 128-pixel tile, both 3xTF32 with the pixel operand in TMEM (thread = pixel = TMEM lane):
+//   MMA1  [128 px x C] . [C x NP]   recompute S, T            A = features (converter warps), B = parameter planes, K-major
+//   MMA2  [128 px x NP] . [NP x C]  the du contraction        A = G (written to TMEM by the derivative warps),
+//                                   B = a second, transposed K-major copy of the parameter planes ([n/4][c][n%4]);
+//                                   N = C (<= 256) columns of TMEM.  (Reading the forward planes through an MN-major
+//                                   descriptor instead was tried first: with the MN-major bit set kind::tf32 returned
+//                                   all-zero accumulators for every (LBO, SBO) candidate -- profiles/r1_k4.md.)
+// One persistent 512-thread CTA per SM, a 3-stage software pipeline over tiles with single-buffered TMEM resources:
+//   warp 0   TMA producer            warp 1   MMA1 issuer          warp 3   MMA2 issuer
+//   warps 4-7    converters: u -> (hi, lo) -> TMEM, |u|^2
+//   warps 8-11   derivative warps: S,T from TMEM, dlogits -> gS, gT, alpha, class scalars; G -> TMEM (+ fp32 planes for K4b)
+//   warps 12-15  output warps: D2 from TMEM, + alpha*u (u re-read, L2 hit), store du
+// The weight gradient dW = G^T.U (K4b) and the finalisation (K4c) stay in head_bwd.cu.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "head_common.cuh"
+#include "head_tc.cuh"
+#include "tc_common.cuh"
+
+namespace halo {
+
+constexpr int BT_BM = 128, BT_BK = 32, BT_HK = 16;
+constexpr int BT_STAGES = 6;
+constexpr int BT_STAGE_FLOATS = BT_BK * BT_BM;
+constexpr int BT_THREADS = 512;
+constexpr int BT_TMEM_COLS = 512;
+// TMEM columns: A halves [0,64) | forward accumulators main, corr [64, 64+2NP) | G hi, lo [.., +2NP) | D2 [256, 256+C)
+constexpr int BT_A_COL = 0, BT_FACC_COL = 64, BT_D2_COL = 256;
+
+struct BwdTcArgs {
+  const float* feat;
+  const float* dlogits;
+  float* dfeat;
+  float* G;         // [N][2OP][HW] fp32 planes for the weight-gradient kernel
+  float* cls_part;  // [grid][3][OP]
+  int N, C, O, HW, tiles_per_img, total_tiles;
+  HeadConsts hc;
+};
+
+struct BtSmem {
+  size_t w2_off, ring_off, bar_off, tmem_off, cls_off, n2_off, alpha_off, red_off, total;
+  int stages;
+};
+__host__ __device__ inline BtSmem bt_smem_layout(int NP, int OP, int C) {
+  BtSmem L;
+  const size_t w_bytes = (size_t)2 * NP * C * 4;      // forward planes (MMA1) and transposed planes (MMA2): same size
+  L.w2_off = (w_bytes + 1023) / 1024 * 1024;
+  L.ring_off = (L.w2_off + w_bytes + 1023) / 1024 * 1024;
+  const size_t tail = 2560;                            // barriers, class constants, |u|^2, alpha, reduction slots
+  const size_t budget = (size_t)227 * 1024;
+  int st = (int)((budget - L.ring_off - tail) / ((size_t)BT_STAGE_FLOATS * 4));
+  L.stages = st > BT_STAGES ? BT_STAGES : st;          // 2 stages at C=256/NP=48, 6 for small heads
+  L.bar_off = L.ring_off + (size_t)L.stages * BT_STAGE_FLOATS * 4;
+  const int nbars = 2 * BT_STAGES + 4 + 2 + 2 + 2;
+  L.tmem_off = L.bar_off + (size_t)nbars * 8;
+  L.cls_off = (L.tmem_off + 16 + 15) / 16 * 16;
+  L.n2_off = L.cls_off + (size_t)4 * OP * 4;
+  L.alpha_off = L.n2_off + BT_BM * 4;
+  L.red_off = L.alpha_off + BT_BM * 4;
+  L.total = L.red_off + (size_t)4 * 3 * OP * 4;
+  return L;
+}
+
+template <int NP, int OP>
+__global__ void __launch_bounds__(BT_THREADS, 1)
+head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, const float* __restrict__ wtc,
+                   const float* __restrict__ w2g) {
+  static_assert(BT_FACC_COL + 4 * NP <= BT_D2_COL, "TMEM column budget");
+  constexpr int G_COL = BT_FACC_COL + 2 * NP;  // G hi at G_COL, lo at G_COL + NP
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int C = a.C;
+  const BtSmem L = bt_smem_layout(NP, OP, C);
+  float* sW = reinterpret_cast<float*>(smem);
+  float* sW2 = reinterpret_cast<float*>(smem + L.w2_off);  // [2][NP/4][C][4]: transposed planes for MMA2
+  float* ring = reinterpret_cast<float*>(smem + L.ring_off);
+  const int NST = L.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + BT_STAGES;
+  uint64_t* a_full = bars + 2 * BT_STAGES;   // [2]
+  uint64_t* a_empty = a_full + 2;            // [2]
+  uint64_t* facc_full = a_empty + 2;         // MMA1 done for a tile
+  uint64_t* facc_empty = facc_full + 1;      // derivative warps have read S,T
+  uint64_t* g_full = facc_empty + 1;         // G (and alpha) of a tile are in TMEM / smem
+  uint64_t* g_empty = g_full + 1;            // MMA2 has consumed G
+  uint64_t* d2_full = g_empty + 1;           // MMA2 done
+  uint64_t* d2_empty = d2_full + 1;          // output warps have read D2 (and alpha)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
+  float* sCls = reinterpret_cast<float*>(smem + L.cls_off);
+  float* sN2 = reinterpret_cast<float*>(smem + L.n2_off);
+  float* sAlpha = reinterpret_cast<float*>(smem + L.alpha_off);
+  float* sRed = reinterpret_cast<float*>(smem + L.red_off);  // [4 warps][3][OP]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const int n4 = 2 * NP * C / 4;
+    const float4* src = reinterpret_cast<const float4*>(wtc);
+    float4* dst = reinterpret_cast<float4*>(sW);
+    for (int i = threadIdx.x; i < n4; i += BT_THREADS) dst[i] = src[i];
+    const float4* src2 = reinterpret_cast<const float4*>(w2g);
+    float4* dst2 = reinterpret_cast<float4*>(sW2);
+    for (int i = threadIdx.x; i < n4; i += BT_THREADS) dst2[i] = src2[i];
+    const float* csrc = wtc + (size_t)2 * NP * C;
+    for (int i = threadIdx.x; i < 4 * OP; i += BT_THREADS) sCls[(i % OP) * 4 + i / OP] = csrc[i];
+    for (int i = threadIdx.x; i < 4 * 3 * OP; i += BT_THREADS) sRed[i] = 0.f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+    mbar_init(facc_full, 1); mbar_init(facc_empty, 4);
+    mbar_init(g_full, 4);    mbar_init(g_empty, 1);
+    mbar_init(d2_full, 1);   mbar_init(d2_empty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BT_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int HW = a.HW;
+  const int cpt = C / BT_BK;
+  const int my_tiles = (blockIdx.x < a.total_tiles) ? (a.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + (size_t)NP * C);
+
+  if (warp == 0) {
+    // =================== TMA producer ===================
+    if (lane == 0) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int tile = blockIdx.x + i * gridDim.x;
+        const int n = tile / a.tiles_per_img;
+        const int p0 = (tile - n * a.tiles_per_img) * BT_BM;
+        for (int j = 0; j < cpt; ++j) {
+          const int q = i * cpt + j;
+          const int s = q % NST;
+          mbar_wait(&empty[s], ((uint32_t)(q / NST) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full[s], BT_STAGE_FLOATS * 4);
+          tma_load_2d(ring + (size_t)s * BT_STAGE_FLOATS, &tmap, p0, n * C + j * BT_BK, &full[s]);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =================== MMA1 issuer: S, T (one main + one correction accumulator) ===================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
+      const uint32_t lbo = NP * 16, sbo = 128;
+      const uint32_t d_main = tmem_base + BT_FACC_COL, d_corr = tmem_base + BT_FACC_COL + NP;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(facc_empty, ((uint32_t)i & 1u) ^ 1u);
+        tc_fence_after();
+        for (int j = 0; j < cpt; ++j) {
+          const int ca = i * cpt + j;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(&a_full[h], (uint32_t)ca & 1u);
+            tc_fence_after();
+            const uint32_t a_col = tmem_base + BT_A_COL + h * 2 * BT_HK;
+#pragma unroll
+            for (int ks = 0; ks < BT_HK / 8; ++ks) {
+              const uint32_t koff = (uint32_t)((j * BT_BK + h * BT_HK + ks * 8) / 4) * lbo;
+              const uint64_t b_hi = make_b_desc(w_hi + koff, lbo, sbo);
+              const uint64_t b_lo = make_b_desc(w_lo + koff, lbo, sbo);
+              const uint32_t first = (j == 0 && h == 0 && ks == 0) ? 0u : 1u;
+              tc_mma_tf32_ts(d_main, a_col + ks * 8, b_hi, idesc, first);
+              tc_mma_tf32_ts(d_corr, a_col + BT_HK + ks * 8, b_hi, idesc, first);
+              tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);
+            }
+            tc_commit(&a_empty[h]);
+          }
+        }
+        tc_commit(facc_full);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // =================== MMA2 issuer: D2[128 x C] = G . W  (B = parameter planes through an MN-major descriptor) =====
+    if (lane == 0) {
+      // D=f32, A=B=tf32, both K-major, N=C, M=128.  B rows = channels (16 B apart), K = n: chunks of 4 n are C*16 B apart
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
+      const uint32_t lbo = (uint32_t)C * 16, sbo = 128;
+      const uint32_t w2_hi = smem_u32(sW2), w2_lo = smem_u32(sW2 + (size_t)NP * C);
+      const uint32_t d2 = tmem_base + BT_D2_COL;
+      for (int i = 0; i < my_tiles; ++i) {
+        mbar_wait(g_full, (uint32_t)i & 1u);
+        mbar_wait(d2_empty, ((uint32_t)i & 1u) ^ 1u);
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < NP / 8; ++ks) {
+          const uint64_t b_hi = make_b_desc(w2_hi + 2 * ks * lbo, lbo, sbo);
+          const uint64_t b_lo = make_b_desc(w2_lo + 2 * ks * lbo, lbo, sbo);
+          const uint32_t g_hi = tmem_base + G_COL + ks * 8, g_lo = g_hi + NP;
+          tc_mma_tf32_ts(d2, g_hi, b_hi, idesc, ks == 0 ? 0u : 1u);
+          tc_mma_tf32_ts(d2, g_lo, b_hi, idesc, 1u);
+          tc_mma_tf32_ts(d2, g_hi, b_lo, idesc, 1u);
+        }
+        tc_commit(g_empty);
+        tc_commit(d2_full);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // =================== converters ===================
+    const int wq = warp & 3, m = wq * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    for (int i = 0; i < my_tiles; ++i) {
+      float n2 = 0.f;
+      for (int j = 0; j < cpt; ++j) {
+        const int ca = i * cpt + j;
+        const int s = ca % NST;
+        mbar_wait(&full[s], (uint32_t)(ca / NST) & 1u);
+        const float* src = ring + (size_t)s * BT_STAGE_FLOATS + m;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(&a_empty[h], ((uint32_t)ca & 1u) ^ 1u);
+          tc_fence_after();
+          uint32_t hi[BT_HK], lo[BT_HK];
+#pragma unroll
+          for (int k = 0; k < BT_HK; ++k) {
+            const float u = src[(h * BT_HK + k) * BT_BM];
+            n2 = fmaf(u, u, n2);
+            const uint32_t hb = cvt_rna_tf32(u);
+            hi[k] = hb;
+            lo[k] = cvt_rna_tf32(u - __uint_as_float(hb));
+          }
+          const uint32_t taddr = tmem_base + lane_addr + BT_A_COL + h * 2 * BT_HK;
+          tmem_st_x16(taddr, hi);
+          tmem_st_x16(taddr + BT_HK, lo);
+          if (j == cpt - 1 && h == 1) {
+            // sN2 of the previous tile was consumed before facc_empty, which MMA1 waited for before this tile's MMAs
+            sN2[m] = n2;
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[h]);
+        }
+        if (lane == 0) mbar_arrive(&empty[s]);
+      }
+    }
+  } else if (warp >= 8 && warp < 12) {
+    // =================== derivative warps (thread = pixel) ===================
+    const int wq = warp & 3, m = wq * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    const HeadConsts hc = a.hc;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int n = tile / a.tiles_per_img;
+      const int p = (tile - n * a.tiles_per_img) * BT_BM + m;
+      const bool live = (p < HW);
+      mbar_wait(facc_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      const float n2 = sN2[m];
+      float S[OP], T[OP];
+      {
+        float buf[2 * OP], cor[2 * OP];
+        const uint32_t taddr = tmem_base + lane_addr + BT_FACC_COL;
+#pragma unroll
+        for (int c8 = 0; c8 < (2 * OP) / 8; ++c8) {
+          tmem_ld_x8(taddr + c8 * 8, *reinterpret_cast<float(*)[8]>(&buf[c8 * 8]));
+          tmem_ld_x8(taddr + NP + c8 * 8, *reinterpret_cast<float(*)[8]>(&cor[c8 * 8]));
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < OP; ++k) { S[k] = buf[k] + cor[k]; T[k] = buf[OP + k] + cor[OP + k]; }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(facc_empty);
+
+      const PixelScalarGrads ps = tangent_scalar_grads(n2, hc);
+      float g_gamma = 0.f, g_t2 = 0.f, g_om = 0.f;
+      float gS[OP], gT[OP];
+#pragma unroll
+      for (int k = 0; k < OP; ++k) {
+        gS[k] = gT[k] = 0.f;
+        float d_pp = 0.f, d_an = 0.f, d_pa = 0.f;
+        if (k < a.O) {
+          const float G = live ? __ldg(a.dlogits + ((size_t)n * a.O + k) * HW + p) : 0.f;
+          const float4 cl = reinterpret_cast<const float4*>(sCls)[k];
+          mlr_logit_grad(G, S[k], T[k], ps, cl.x, cl.y, cl.z, cl.w, hc, gS[k], gT[k], g_gamma, g_t2, g_om, d_pp, d_an, d_pa);
+        }
+        // class scalars: fixed-order warp reduction into this warp's slot
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          d_pp += __shfl_xor_sync(0xffffffffu, d_pp, o);
+          d_an += __shfl_xor_sync(0xffffffffu, d_an, o);
+          d_pa += __shfl_xor_sync(0xffffffffu, d_pa, o);
+        }
+        if (lane == 0) {
+          sRed[(wq * 3 + 0) * OP + k] += d_pp;
+          sRed[(wq * 3 + 1) * OP + k] += d_an;
+          sRed[(wq * 3 + 2) * OP + k] += d_pa;
+        }
+      }
+      const float alpha = 2.f * (g_gamma * ps.dgam + g_t2 * ps.dt2 + g_om * ps.dom);
+      // fp32 G planes for the weight-gradient kernel
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < OP; ++k) {
+          a.G[((size_t)n * 2 * OP + k) * HW + p] = gS[k];
+          a.G[((size_t)n * 2 * OP + OP + k) * HW + p] = gT[k];
+        }
+      }
+      // G -> TMEM (hi, lo), columns n = [gS (OP) | gT (OP) | zeros up to NP]
+      mbar_wait(g_empty, ((uint32_t)i & 1u) ^ 1u);   // MMA2 of the previous tile has consumed G
+      mbar_wait(d2_empty, ((uint32_t)i & 1u) ^ 1u);  // ... and the output warps are done with sAlpha
+      tc_fence_after();
+      {
+        float gv[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) gv[k] = 0.f;   // columns >= 2*OP multiply zero parameter rows but must be finite
+#pragma unroll
+        for (int k = 0; k < OP; ++k) { gv[k] = gS[k]; gv[OP + k] = gT[k]; }
+        const uint32_t taddr = tmem_base + lane_addr + G_COL;
+#pragma unroll
+        for (int c16 = 0; c16 < NP / 16; ++c16) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float v = gv[c16 * 16 + e];
+            const uint32_t hb = cvt_rna_tf32(v);
+            hi[e] = hb;
+            lo[e] = cvt_rna_tf32(v - __uint_as_float(hb));
+          }
+          tmem_st_x16(taddr + c16 * 16, hi);
+          tmem_st_x16(taddr + NP + c16 * 16, lo);
+        }
+      }
+      sAlpha[m] = alpha;
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_full);
+    }
+  } else if (warp >= 12) {
+    // =================== output warps (thread = pixel): du = D2 + alpha * u ===================
+    const int wq = warp & 3, m = wq * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int n = tile / a.tiles_per_img;
+      const int p = (tile - n * a.tiles_per_img) * BT_BM + m;
+      const bool live = (p < HW);
+      const float* ubase = a.feat + (size_t)n * C * HW + p;
+      float* dbase = a.dfeat + (size_t)n * C * HW + p;
+      mbar_wait(d2_full, (uint32_t)i & 1u);
+      tc_fence_after();
+      const float alpha = sAlpha[m];
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        float d[32];
+        tmem_ld_x32(tmem_base + lane_addr + BT_D2_COL + c0, d);
+        float u[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) u[e] = live ? __ldg(ubase + (size_t)(c0 + e) * HW) : 0.f;
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (live) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) __stcs(dbase + (size_t)(c0 + e) * HW, fmaf(alpha, u[e], d[e]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty);
+    }
+  }
+  // ---- teardown ----
+  tc_fence_before();
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * OP; i += BT_THREADS) {
+    float s = 0.f;
+    for (int w = 0; w < 4; ++w) s += sRed[w * 3 * OP + i];
+    a.cls_part[(size_t)blockIdx.x * 3 * OP + i] = s;
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BT_TMEM_COLS) : "memory");
+  }
+}
+
+// transposed parameter planes for MMA2: [2 (hi,lo)][NP/4][C][4], value(c, n) = Wt[c][n] of the CUDA-core pack (0 for n >= 2*OP)
+__global__ void head_pack_bwd_planes_kernel(const float* __restrict__ std_pack, float* __restrict__ w2, int C, int OP, int NP) {
+  const int KP = 2 * OP, total = NP * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int n4 = i / (C * 4), rem = i - n4 * C * 4;
+    const int ch = rem >> 2, n = n4 * 4 + (rem & 3);
+    const float w = (n < KP) ? std_pack[(size_t)ch * KP + n] : 0.f;
+    const uint32_t h = cvt_rna_tf32(w);
+    w2[i] = __uint_as_float(h);
+    w2[(size_t)total + i] = __uint_as_float(cvt_rna_tf32(w - __uint_as_float(h)));
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+bool head_bwd_tc_supported(int C, int O, int H, int W, const void* feat, const void* dfeat) {
+  if (C % BT_BK != 0 || C > 256 || C < BT_BK || C % 16 != 0) return false;
+  const int NP = round_up(2 * head_op_pad(O), 16);
+  if (BT_FACC_COL + 4 * NP > BT_D2_COL) return false;  // O <= 24
+  if (((long long)H * W) % 4 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(feat) & 15) != 0) return false;
+  const BtSmem L = bt_smem_layout(NP, head_op_pad(O), C);
+  if (L.stages < 2 || L.total > 227 * 1024) return false;
+  return get_encode_fn() != nullptr;
+}
+
+int head_bwd_tc_grid(int N, int HW) {
+  const int tiles = ((HW + BT_BM - 1) / BT_BM) * N;
+  int g = sm_count();
+  return g < tiles ? g : tiles;
+}
+
+template <int NP, int OP>
+static int launch_bwd_tc(const CUtensorMap& tmap, const BwdTcArgs& a, const float* wtc, const float* w2, size_t smem, int grid,
+                         cudaStream_t st) {
+  HALO_CUDA(cudaFuncSetAttribute(head_bwd_tc_kernel<NP, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  head_bwd_tc_kernel<NP, OP><<<grid, BT_THREADS, smem, st>>>(tmap, a, wtc, w2);
+  return launch_status("head_bwd_tc_kernel");
+}
+
+// wtc: tensor-core parameter pack (head_pack_tc_kernel layout); G, cls_part: as in head_bwd.cu
+int head_bwd_tc_launch(const float* feat, const float* dlogits, float* dfeat, float* G, float* cls_part, const float* std_pack,
+                       const float* wtc, float* w2, float c, int N, int C, int O, int H, int W, int grid, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled unavailable");
+    return HALO_ERR_CUDA;
+  }
+  const int OP = head_op_pad(O), NP = round_up(2 * OP, 16), HW = H * W;
+  head_pack_bwd_planes_kernel<<<(NP * C + 255) / 256, 256, 0, st>>>(std_pack, w2, C, OP, NP);
+  {
+    int rc = launch_status("head_pack_bwd_planes_kernel");
+    if (rc) return rc;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)HW, (cuuint64_t)N * C};
+  const cuuint64_t gstride[1] = {(cuuint64_t)HW * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)BT_BM, (cuuint32_t)BT_BK};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(feat), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return HALO_ERR_CUDA;
+  }
+  BwdTcArgs a;
+  a.feat = feat; a.dlogits = dlogits; a.dfeat = dfeat; a.G = G; a.cls_part = cls_part;
+  a.N = N; a.C = C; a.O = O; a.HW = HW;
+  a.tiles_per_img = (HW + BT_BM - 1) / BT_BM;
+  a.total_tiles = a.tiles_per_img * N;
+  a.hc = make_head_consts(c);
+  const BtSmem L = bt_smem_layout(NP, OP, C);
+  switch (OP) {
+    case 4: return launch_bwd_tc<16, 4>(tmap, a, wtc, w2, L.total, grid, st);
+    case 8: return launch_bwd_tc<16, 8>(tmap, a, wtc, w2, L.total, grid, st);
+    case 12: return launch_bwd_tc<32, 12>(tmap, a, wtc, w2, L.total, grid, st);
+    case 16: return launch_bwd_tc<32, 16>(tmap, a, wtc, w2, L.total, grid, st);
+    case 20: return launch_bwd_tc<48, 20>(tmap, a, wtc, w2, L.total, grid, st);
+    default: return launch_bwd_tc<48, 24>(tmap, a, wtc, w2, L.total, grid, st);
+  }
+}
+
+}  // namespace halo

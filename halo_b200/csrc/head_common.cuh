@@ -184,6 +184,88 @@ __device__ __forceinline__ void softmax_stats(const float (&l)[OP], int O, const
   label = (label_mode == HALO_LABEL_GT_FILLED) ? gtf : arg;
 }
 
+// ---- analytic derivative of the epilogue (shared by the CUDA-core and tensor-core backward kernels) -----------
+struct PixelScalarGrads {
+  float gamma, t2, omega;   // as in PixelScalars
+  float dgam, dt2, dom;     // d/d(n2) of gamma, t2 = c|x|^2, omega = 1 - c|x|^2
+};
+
+__device__ __forceinline__ PixelScalarGrads tangent_scalar_grads(float n2, const HeadConsts& hc) {
+  PixelScalarGrads g;
+  const float nn = sqrtf(n2);
+  const float nsafe = fmaxf(nn, 1e-15f);
+  const float sn = hc.s * nn;
+  const bool clipped = sn > hc.z_clip;
+  const float z = fminf(sn, hc.z_clip);
+  const float e = expf(-2.f * z);
+  const float t = clipped ? hc.t_clip : tanhf(z);
+  const float ope = 1.f + e;
+  g.omega = clipped ? hc.omega_clip : 4.f * e / (ope * ope);
+  g.gamma = t / (hc.s * nsafe);
+  g.t2 = t * t;
+  if (clipped) {  // project(): x = u/|u| * maxnorm, only the direction carries gradient
+    g.dgam = -g.gamma / (2.f * fmaxf(n2, 1e-30f));
+    g.dt2 = 0.f;
+    g.dom = 0.f;
+  } else {
+    g.dgam = (z < 1e-3f) ? (-hc.c * (1.f / 3.f)) : (g.omega - g.gamma) / (2.f * fmaxf(n2, 1e-30f));
+    g.dt2 = t * hc.s * g.omega / nsafe;
+    g.dom = -t * g.omega * hc.s / nsafe;
+    if (nn < 1e-15f) { g.dt2 = hc.c; g.dom = -hc.c; }  // limits at the origin
+  }
+  return g;
+}
+
+// One class: upstream gradient G of the logit -> gradients w.r.t. the two contractions (gS, gT), accumulated
+// gradients w.r.t. the per-pixel scalars (g_gamma, g_t2, g_om) and the class scalars (d_pp, d_an, d_pa).
+__device__ __forceinline__ void mlr_logit_grad(float G, float S, float T, const PixelScalarGrads& ps, float pp, float an,
+                                               float pa, float Bk, const HeadConsts& hc, float& gS, float& gT,
+                                               float& g_gamma, float& g_t2, float& g_om, float& d_pp, float& d_an,
+                                               float& d_pa) {
+  const float px = ps.gamma * S, xa = ps.gamma * T;
+  const float cpx2 = 2.f * hc.c * px;
+  const float Anum = 1.f + cpx2 + ps.t2;
+  const float Draw = 1.f + cpx2 + hc.c * ps.t2 * pp;
+  const bool dclamp = Draw < 1e-12f;
+  const float D = dclamp ? 1e-12f : Draw;
+  const float num = Bk * xa + Anum * pa;
+  const float bo = Bk * ps.omega;
+  const float omc = bo / D;
+  float arg, a_num, a_bo, a_D;
+  if (omc >= hc.om_max) {
+    const float den = fmaxf(bo, 1e-12f * D);
+    arg = hc.two_s * num / den;
+    a_num = hc.two_s / den;
+    a_bo = -arg / den;
+    a_D = 0.f;
+  } else {
+    const float m = fmaxf(1.f - omc, 0.f) * hc.inv_c;
+    const float root = fmaxf(sqrtf(m), 1e-12f);
+    const float invD = 1.f / D;
+    arg = num * invD * (hc.out_scale / root);
+    a_num = invD * (hc.out_scale / root);
+    const float a_m = -arg / (2.f * root * root);  // d arg / d m  (through 1/root)
+    a_bo = a_m * (-invD * hc.inv_c);
+    a_D = -arg * invD + a_m * (omc * invD * hc.inv_c);
+  }
+  const float ash = asinhf(arg);
+  const float g = G * hc.two_over_s * an * rsqrtf(1.f + arg * arg);
+  const float g_num = g * a_num, g_bo = g * a_bo, g_D = dclamp ? 0.f : g * a_D;
+  const float g_Bk = g_num * xa + g_bo * ps.omega;
+  const float g_xa = g_num * Bk;
+  const float g_Anum = g_num * pa;
+  const float g_cpx2 = g_Anum + g_D;
+  g_t2 += g_Anum + g_D * hc.c * pp;
+  g_om += g_bo * Bk;
+  const float g_px = 2.f * hc.c * g_cpx2;
+  g_gamma += g_px * S + g_xa * T;
+  gS = g_px * ps.gamma;
+  gT = g_xa * ps.gamma;
+  d_pp += g_D * hc.c * ps.t2 - hc.c * g_Bk;
+  d_an += G * hc.two_over_s * ash;
+  d_pa += g_num * Anum;
+}
+
 // arguments shared by the CUDA-core and tensor-core forward kernels
 struct HeadArgs {
   const void* feat;

@@ -11,4 +11,13 @@ size_t head_tc_pack_floats(int O, int C);
 // packs the class parameters into the tensor-core layout and launches the kernel on `st`
 int head_fwd_tc_launch(HeadArgs a, const float* std_pack, float* wtc, cudaStream_t st);
 
+// std pack (head_pack_kernel) -> tensor-core operand planes
+int head_pack_tc_launch(const float* std_pack, float* wtc, int C, int CPAD, int O, cudaStream_t st);
+
+// tensor-core pixel pass of the backward (head_bwd_tc.cu)
+bool head_bwd_tc_supported(int C, int O, int H, int W, const void* feat, const void* dfeat);
+int head_bwd_tc_grid(int N, int HW);
+int head_bwd_tc_launch(const float* feat, const float* dlogits, float* dfeat, float* G, float* cls_part, const float* std_pack,
+                       const float* wtc, float* w2, float c, int N, int C, int O, int H, int W, int grid, cudaStream_t st);
+
 }  // namespace halo

@@ -92,3 +92,20 @@ def head_grads(u, P, A, dlogits, c=1.0):
     out = mlr_logits(x.double(), P, A, c).float()
     du, dP, dA = torch.autograd.grad(out, (u, P, A), grad_outputs=dlogits.float())
     return du, dP, dA
+
+
+def nonsmooth_pixels(u, P, c=1.0, rel=1e-5):
+    """(B,H,W) bool: pixels where some class sits within `rel` (relative, in 1 - c*m) of the MLR's projection
+    switch root == maxnorm (hyperbolic.py:163-170).  The two `where`s make the logit continuous but its derivative
+    discontinuous there, so an fp32 recompute may legitimately take the other branch than fp64 autograd
+    (SURVEY a-14 "non-smooth points"); gradient parity tests leave these pixels out of the du comparison."""
+    K = float(c)
+    x = expmap(u, c, dim=1).double()
+    q = -P.double()
+    xx = (x * x).sum(dim=1, keepdim=True)
+    pp = (q * q).sum(dim=1)[None, :, None, None]
+    px = torch.einsum("bchw,oc->bohw", x, q)
+    den = torch.clamp(1 + 2 * K * px + K * K * xx * pp, min=1e-12)
+    one_minus_cm = (1 - K * pp) * (1 - K * xx) / den  # the Mobius-norm identity, DESIGN.md section 4
+    thresh = 1 - (1.0 - PROJ_EPS_MLR) ** 2
+    return ((one_minus_cm / thresh - 1).abs() < rel).any(dim=1)
