@@ -215,7 +215,7 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
     const int wq = warp & 3, m = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
     for (int i = 0; i < my_tiles; ++i) {
-      float n2 = 0.f;
+      unsigned long long n2 = 0ull;
       for (int j = 0; j < cpt; ++j) {
         const int ca = i * cpt + j;
         const int s = ca % NST;
@@ -226,20 +226,13 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
           mbar_wait(&a_empty[h], ((uint32_t)ca & 1u) ^ 1u);
           tc_fence_after();
           uint32_t hi[BT_HK], lo[BT_HK];
-#pragma unroll
-          for (int k = 0; k < BT_HK; ++k) {
-            const float u = src[(h * BT_HK + k) * BT_BM];
-            n2 = fmaf(u, u, n2);
-            const uint32_t hb = cvt_rna_tf32(u);
-            hi[k] = hb;
-            lo[k] = cvt_rna_tf32(u - __uint_as_float(hb));
-          }
+          tc_split16(src + h * BT_HK * BT_BM, BT_BM, hi, lo, n2);
           const uint32_t taddr = tmem_base + lane_addr + BT_A_COL + h * 2 * BT_HK;
           tmem_st_x16(taddr, hi);
           tmem_st_x16(taddr + BT_HK, lo);
           if (j == cpt - 1 && h == 1) {
             // sN2 of the previous tile was consumed before facc_empty, which MMA1 waited for before this tile's MMAs
-            sN2[m] = n2;
+            sN2[m] = n2_of(n2);
           }
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();

@@ -215,7 +215,7 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
     for (int i = g; i < my_tiles; i += TC_NWG) {
       const int it = i / TC_NWG;
-      float n2 = 0.f;
+      unsigned long long n2 = 0ull;  // two fp32 partial sums of |u|^2
       for (int j = 0; j < cpt; ++j) {
         const int ca = it * cpt + j;                        // stage counter of this warpgroup
         const int s = g * TC_WG_STAGES + ca % TC_WG_STAGES;
@@ -226,20 +226,13 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
           mbar_wait(&a_empty[g * 2 + h], ((uint32_t)ca & 1u) ^ 1u);
           tc_fence_after();
           uint32_t hi[TC_HK], lo[TC_HK];
-#pragma unroll
-          for (int k = 0; k < TC_HK; ++k) {
-            const float u = src[(h * TC_HK + k) * TC_BM];
-            n2 = fmaf(u, u, n2);
-            const uint32_t hbits = cvt_rna_tf32(u);
-            hi[k] = hbits;
-            lo[k] = cvt_rna_tf32(u - __uint_as_float(hbits));
-          }
+          tc_split16(src + h * TC_HK * TC_BM, TC_BM, hi, lo, n2);
           const uint32_t taddr = tmem_base + lane_addr + (g * 2 + h) * TC_ACOLS;
           tmem_st_x16(taddr, hi);
           tmem_st_x16(taddr + TC_HK, lo);
           // |u|^2 travels to the epilogue warpgroup through shared memory; it is published by the release of the
           // tile's last a_full arrival (-> MMA issuer -> tcgen05.commit -> acc_full acquire in the epilogue)
-          if (j == cpt - 1 && h == 1) sN2[g * TC_BM + m] = n2;
+          if (j == cpt - 1 && h == 1) sN2[g * TC_BM + m] = n2_of(n2);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();

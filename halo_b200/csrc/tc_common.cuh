@@ -62,6 +62,37 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
 // on sm_100a (profiles/r1_k1_tc.md).  Sign-magnitude bits: adding half an ulp of the 10-bit mantissa to the
 // magnitude and clearing the 13 low bits rounds correctly for both signs (inf/NaN inputs stay non-finite).
 __device__ __forceinline__ uint32_t cvt_rna_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// 16 feature values of one pixel (channel stride `stride` floats) -> TF32 hi (round-to-nearest) and the exact
+// remainder lo = u - hi, plus |u|^2 accumulated in two fp32 lanes.  The remainder is NOT re-rounded: it has <= 13
+// significant bits and the tensor core reads the top 10 of them (absolute error <= 2^-21 |u|, unbiased in sign) --
+// measured equal to the rounded variant in tools/tc_numerics.py.  The two fp32 subtractions / multiply-adds of a
+// channel pair issue as one packed FADD2 / FFMA2 (sm_100a), so a pair costs 2 LDS + 2 IADD + 2 LOP + FADD2 + FFMA2
+// instead of 14 instructions.
+__device__ __forceinline__ unsigned long long pack_f32x2(uint32_t a, uint32_t b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void tc_split16(const float* __restrict__ src, int stride, uint32_t (&hi)[16], uint32_t (&lo)[16],
+                                           unsigned long long& n2acc) {
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const uint32_t u0 = __float_as_uint(src[k * stride]), u1 = __float_as_uint(src[(k + 1) * stride]);
+    const unsigned long long uu = pack_f32x2(u0, u1);
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(n2acc) : "l"(uu));
+    const uint32_t h0 = (u0 + 0x1000u) & 0xffffe000u, h1 = (u1 + 0x1000u) & 0xffffe000u;
+    unsigned long long ll;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(ll) : "l"(uu), "l"(pack_f32x2(h0, h1)));
+    hi[k] = h0;
+    hi[k + 1] = h1;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(lo[k]), "=r"(lo[k + 1]) : "l"(ll));
+  }
+}
+__device__ __forceinline__ float n2_of(unsigned long long n2acc) {
+  uint32_t a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(n2acc));
+  return __uint_as_float(a) + __uint_as_float(b);
+}
 __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "

@@ -90,7 +90,7 @@ def test_tensor_core_path_shapes(shape):
                                 label_mode="gt_filled", tensor_cores=False)
     assert rel_err(tc["logits"], logits) <= TOL
     assert rel_err(tc["radius"], rad) <= TOL
-    assert torch.equal(tc["radius"], cc["radius"])                 # |u|^2 is accumulated in the same order on both paths
+    assert rel_err(tc["radius"], cc["radius"]) <= 2e-6             # |u|^2: two interleaved fp32 partial sums (FFMA2) vs one chain
     assert torch.allclose(tc["stats"][:, :2], cc["stats"][:, :2])
     assert rel_err(tc["pixunc"], cc["pixunc"]) <= 1e-4
     assert (tc["label"] == cc["label"]).float().mean().item() >= 0.999
