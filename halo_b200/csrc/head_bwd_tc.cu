@@ -4,16 +4,19 @@
 //
 // Two chained GEMMs per 128-pixel tile, both 3xTF32 with the pixel operand in TMEM (thread = pixel = TMEM lane):
 //   MMA1  [128 px x C] . [C x NP]   recompute S, T            A = features (converter warps), B = parameter planes, K-major
-//   MMA2  [128 px x NP] . [NP x C]  the du contraction        A = G (written to TMEM by the derivative warps),
-//                                   B = a second, transposed K-major copy of the parameter planes ([n/4][c][n%4]);
-//                                   N = C (<= 256) columns of TMEM.  (Reading the forward planes through an MN-major
-//                                   descriptor instead was tried first: with the MN-major bit set kind::tf32 returned
-//                                   all-zero accumulators for every (LBO, SBO) candidate -- profiles/r1_k4.md.)
-// One persistent 512-thread CTA per SM, a 3-stage software pipeline over tiles with single-buffered TMEM resources:
+//   MMA2  [128 px x NR] . [NR x C]  the du contraction        A = G, written by the derivative warps IN PLACE over the S, T
+//                                   accumulators (hi over "main", lo over "correction"); B = a second, transposed
+//                                   K-major copy of the parameter planes ([n/4][c][n%4]); N = C (<= 256) TMEM columns.
+//                                   (Reading the forward planes through an MN-major descriptor instead was tried first:
+//                                   with the MN-major bit set kind::tf32 returned all-zero accumulators -- profiles/r1_k4.md.)
+// One persistent 512-thread CTA per SM; the S,T/G region of TMEM is double-buffered by tile parity so that MMA1 of tile
+// i+1 overlaps the derivative math of tile i:
 //   warp 0   TMA producer            warp 1   MMA1 issuer          warp 3   MMA2 issuer
 //   warps 4-7    converters: u -> (hi, lo) -> TMEM, |u|^2
-//   warps 8-11   derivative warps: S,T from TMEM, dlogits -> gS, gT, alpha, class scalars; G -> TMEM (+ fp32 planes for K4b)
-//   warps 12-15  output warps: D2 from TMEM, + alpha*u (u re-read, L2 hit), store du
+//   warps 8-11   derivative warps: S,T from TMEM four classes at a time (a ROLLED loop: the fully unrolled 20-class
+//                body was 128 KB of SASS and ran at IPC 0.15 on instruction-cache misses), dlogits -> gS, gT, alpha,
+//                class scalars; G -> TMEM (+ fp32 planes for K4b)
+//   warps 12-15  output warps: D2 from TMEM, + alpha*u (u re-read with one channel group of loads in flight), store du
 // The weight gradient dW = G^T.U (K4b) and the finalisation (K4c) stay in head_bwd.cu.
 #include <cuda.h>
 #include <stdlib.h>
@@ -30,8 +33,8 @@ constexpr int BT_STAGES = 6;
 constexpr int BT_STAGE_FLOATS = BT_BK * BT_BM;
 constexpr int BT_THREADS = 512;
 constexpr int BT_TMEM_COLS = 512;
-// TMEM columns: A halves [0,64) | forward accumulators main, corr [64, 64+2NP) | G hi, lo [.., +2NP) | D2 [256, 256+C)
-constexpr int BT_A_COL = 0, BT_FACC_COL = 64, BT_D2_COL = 256;
+// TMEM columns: A halves [0,64) | S,T -> G region of even tiles [64, 64+2NP) | of odd tiles [.., +2NP) | D2 [256, 256+C)
+constexpr int BT_A_COL = 0, BT_FG_COL = 64, BT_D2_COL = 256;
 
 struct BwdTcArgs {
   const float* feat;
@@ -49,20 +52,21 @@ struct BtSmem {
 };
 __host__ __device__ inline BtSmem bt_smem_layout(int NP, int OP, int C) {
   BtSmem L;
-  const size_t w_bytes = (size_t)2 * NP * C * 4;      // forward planes (MMA1) and transposed planes (MMA2): same size
+  (void)NP;
+  const size_t w_bytes = (size_t)2 * (2 * OP) * C * 4;  // forward planes (MMA1) and transposed planes (MMA2): same size, 2*OP stored rows
   L.w2_off = (w_bytes + 1023) / 1024 * 1024;
   L.ring_off = (L.w2_off + w_bytes + 1023) / 1024 * 1024;
-  const size_t tail = 2560;                            // barriers, class constants, |u|^2, alpha, reduction slots
+  const size_t tail = 4096;                            // barriers, class constants, |u|^2, alpha, reduction slots
   const size_t budget = (size_t)227 * 1024;
   int st = (int)((budget - L.ring_off - tail) / ((size_t)BT_STAGE_FLOATS * 4));
-  L.stages = st > BT_STAGES ? BT_STAGES : st;          // 2 stages at C=256/NP=48, 6 for small heads
+  L.stages = st > BT_STAGES ? BT_STAGES : st;          // 3 stages at C=256/O=19, 6 for small heads
   L.bar_off = L.ring_off + (size_t)L.stages * BT_STAGE_FLOATS * 4;
-  const int nbars = 2 * BT_STAGES + 4 + 2 + 2 + 2;
+  const int nbars = 2 * BT_STAGES + 4 + 6 + 2 + 2;
   L.tmem_off = L.bar_off + (size_t)nbars * 8;
   L.cls_off = (L.tmem_off + 16 + 15) / 16 * 16;
   L.n2_off = L.cls_off + (size_t)4 * OP * 4;
-  L.alpha_off = L.n2_off + BT_BM * 4;
-  L.red_off = L.alpha_off + BT_BM * 4;
+  L.alpha_off = L.n2_off + 2 * BT_BM * 4;              // |u|^2 and alpha are double-buffered by tile parity
+  L.red_off = L.alpha_off + 2 * BT_BM * 4;
   L.total = L.red_off + (size_t)4 * 3 * OP * 4;
   return L;
 }
@@ -71,13 +75,13 @@ template <int NP, int OP>
 __global__ void __launch_bounds__(BT_THREADS, 1)
 head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, const float* __restrict__ wtc,
                    const float* __restrict__ w2g) {
-  static_assert(BT_FACC_COL + 4 * NP <= BT_D2_COL, "TMEM column budget");
-  constexpr int G_COL = BT_FACC_COL + 2 * NP;  // G hi at G_COL, lo at G_COL + NP
+  static_assert(BT_FG_COL + 4 * NP <= BT_D2_COL, "TMEM column budget");
+  constexpr int NR = 2 * OP;                   // stored parameter rows (head_pack_tc_kernel) = K extent of MMA2
   extern __shared__ __align__(1024) unsigned char smem[];
   const int C = a.C;
   const BtSmem L = bt_smem_layout(NP, OP, C);
   float* sW = reinterpret_cast<float*>(smem);
-  float* sW2 = reinterpret_cast<float*>(smem + L.w2_off);  // [2][NP/4][C][4]: transposed planes for MMA2
+  float* sW2 = reinterpret_cast<float*>(smem + L.w2_off);  // [2][NR/4][C][4]: transposed planes for MMA2
   float* ring = reinterpret_cast<float*>(smem + L.ring_off);
   const int NST = L.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
@@ -85,36 +89,38 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
   uint64_t* empty = bars + BT_STAGES;
   uint64_t* a_full = bars + 2 * BT_STAGES;   // [2]
   uint64_t* a_empty = a_full + 2;            // [2]
-  uint64_t* facc_full = a_empty + 2;         // MMA1 done for a tile
-  uint64_t* facc_empty = facc_full + 1;      // derivative warps have read S,T
-  uint64_t* g_full = facc_empty + 1;         // G (and alpha) of a tile are in TMEM / smem
-  uint64_t* g_empty = g_full + 1;            // MMA2 has consumed G
-  uint64_t* d2_full = g_empty + 1;           // MMA2 done
-  uint64_t* d2_empty = d2_full + 1;          // output warps have read D2 (and alpha)
+  uint64_t* facc_full = a_empty + 2;         // [2] MMA1 done for a tile of that parity
+  uint64_t* g_full = facc_full + 2;          // [2] G (and alpha) of a tile are in TMEM / smem
+  uint64_t* g_empty = g_full + 2;            // [2] MMA2 has consumed G: the region may take the S,T of tile i+2
+  uint64_t* d2_full = g_empty + 2;           // MMA2 done
+  uint64_t* d2_empty = d2_full + 1;          // output warps have read D2
+  uint64_t* alpha_free = d2_empty + 1;       // [2] output warps have read sAlpha of a tile of that parity
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
   float* sCls = reinterpret_cast<float*>(smem + L.cls_off);
-  float* sN2 = reinterpret_cast<float*>(smem + L.n2_off);
-  float* sAlpha = reinterpret_cast<float*>(smem + L.alpha_off);
+  float* sN2 = reinterpret_cast<float*>(smem + L.n2_off);      // [2][128]
+  float* sAlpha = reinterpret_cast<float*>(smem + L.alpha_off);  // [2][128]
   float* sRed = reinterpret_cast<float*>(smem + L.red_off);  // [4 warps][3][OP]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   {
-    const int n4 = 2 * NP * C / 4;
+    const int n4 = 2 * NR * C / 4;
     const float4* src = reinterpret_cast<const float4*>(wtc);
     float4* dst = reinterpret_cast<float4*>(sW);
     for (int i = threadIdx.x; i < n4; i += BT_THREADS) dst[i] = src[i];
     const float4* src2 = reinterpret_cast<const float4*>(w2g);
     float4* dst2 = reinterpret_cast<float4*>(sW2);
     for (int i = threadIdx.x; i < n4; i += BT_THREADS) dst2[i] = src2[i];
-    const float* csrc = wtc + (size_t)2 * NP * C;
+    const float* csrc = wtc + (size_t)2 * NR * C;
     for (int i = threadIdx.x; i < 4 * OP; i += BT_THREADS) sCls[(i % OP) * 4 + i / OP] = csrc[i];
     for (int i = threadIdx.x; i < 4 * 3 * OP; i += BT_THREADS) sRed[i] = 0.f;
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 4); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
-    mbar_init(facc_full, 1); mbar_init(facc_empty, 4);
-    mbar_init(g_full, 4);    mbar_init(g_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1);
+      mbar_init(&facc_full[i], 1); mbar_init(&g_full[i], 4); mbar_init(&g_empty[i], 1);
+      mbar_init(&alpha_free[i], 4);
+    }
     mbar_init(d2_full, 1);   mbar_init(d2_empty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -132,21 +138,23 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
   const int HW = a.HW;
   const int cpt = C / BT_BK;
   const int my_tiles = (blockIdx.x < a.total_tiles) ? (a.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + (size_t)NP * C);
+  const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + (size_t)NR * C);
 
   if (warp == 0) {
     // =================== TMA producer ===================
     if (lane == 0) {
+      const uint64_t pol = l2_policy_evict_last();
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int tile = blockIdx.x + i * gridDim.x;
         const int n = tile / a.tiles_per_img;
         const int p0 = (tile - n * a.tiles_per_img) * BT_BM;
         for (int j = 0; j < cpt; ++j) {
-          const int q = i * cpt + j;
-          const int s = q % NST;
-          mbar_wait(&empty[s], ((uint32_t)(q / NST) & 1u) ^ 1u);
+          mbar_wait(&empty[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full[s], BT_STAGE_FLOATS * 4);
-          tma_load_2d(ring + (size_t)s * BT_STAGE_FLOATS, &tmap, p0, n * C + j * BT_BK, &full[s]);
+          tma_load_2d_hint(ring + (size_t)s * BT_STAGE_FLOATS, &tmap, p0, n * C + j * BT_BK, &full[s], pol);
+          if (++s == NST) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -155,10 +163,11 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
     // =================== MMA1 issuer: S, T (one main + one correction accumulator) ===================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
-      const uint32_t lbo = NP * 16, sbo = 128;
-      const uint32_t d_main = tmem_base + BT_FACC_COL, d_corr = tmem_base + BT_FACC_COL + NP;
+      const uint32_t lbo = NR * 16, sbo = 128;
       for (int i = 0; i < my_tiles; ++i) {
-        mbar_wait(facc_empty, ((uint32_t)i & 1u) ^ 1u);
+        const int b = i & 1;
+        const uint32_t d_main = tmem_base + BT_FG_COL + b * 2 * NP, d_corr = d_main + NP;
+        mbar_wait(&g_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);   // MMA2 of tile i-2 has read the region
         tc_fence_after();
         for (int j = 0; j < cpt; ++j) {
           const int ca = i * cpt + j;
@@ -180,32 +189,34 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
             tc_commit(&a_empty[h]);
           }
         }
-        tc_commit(facc_full);
+        tc_commit(&facc_full[b]);
       }
     }
     __syncwarp();
   } else if (warp == 3) {
-    // =================== MMA2 issuer: D2[128 x C] = G . W  (B = parameter planes through an MN-major descriptor) =====
+    // =================== MMA2 issuer: D2[128 x C] = G . W ===================
     if (lane == 0) {
       // D=f32, A=B=tf32, both K-major, N=C, M=128.  B rows = channels (16 B apart), K = n: chunks of 4 n are C*16 B apart
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
       const uint32_t lbo = (uint32_t)C * 16, sbo = 128;
-      const uint32_t w2_hi = smem_u32(sW2), w2_lo = smem_u32(sW2 + (size_t)NP * C);
+      const uint32_t w2_hi = smem_u32(sW2), w2_lo = smem_u32(sW2 + (size_t)NR * C);
       const uint32_t d2 = tmem_base + BT_D2_COL;
       for (int i = 0; i < my_tiles; ++i) {
-        mbar_wait(g_full, (uint32_t)i & 1u);
+        const int b = i & 1;
+        mbar_wait(&g_full[b], (uint32_t)(i >> 1) & 1u);
         mbar_wait(d2_empty, ((uint32_t)i & 1u) ^ 1u);
         tc_fence_after();
+        const uint32_t g_col = tmem_base + BT_FG_COL + b * 2 * NP;
 #pragma unroll
-        for (int ks = 0; ks < NP / 8; ++ks) {
+        for (int ks = 0; ks < NR / 8; ++ks) {
           const uint64_t b_hi = make_b_desc(w2_hi + 2 * ks * lbo, lbo, sbo);
           const uint64_t b_lo = make_b_desc(w2_lo + 2 * ks * lbo, lbo, sbo);
-          const uint32_t g_hi = tmem_base + G_COL + ks * 8, g_lo = g_hi + NP;
+          const uint32_t g_hi = g_col + ks * 8, g_lo = g_hi + NP;
           tc_mma_tf32_ts(d2, g_hi, b_hi, idesc, ks == 0 ? 0u : 1u);
           tc_mma_tf32_ts(d2, g_lo, b_hi, idesc, 1u);
           tc_mma_tf32_ts(d2, g_hi, b_lo, idesc, 1u);
         }
-        tc_commit(g_empty);
+        tc_commit(&g_empty[b]);
         tc_commit(d2_full);
       }
     }
@@ -214,12 +225,13 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
     // =================== converters ===================
     const int wq = warp & 3, m = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    int s = 0;
+    uint32_t ph = 0;
     for (int i = 0; i < my_tiles; ++i) {
       unsigned long long n2 = 0ull;
       for (int j = 0; j < cpt; ++j) {
         const int ca = i * cpt + j;
-        const int s = ca % NST;
-        mbar_wait(&full[s], (uint32_t)(ca / NST) & 1u);
+        mbar_wait(&full[s], ph);
         const float* src = ring + (size_t)s * BT_STAGE_FLOATS + m;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -230,16 +242,16 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
           const uint32_t taddr = tmem_base + lane_addr + BT_A_COL + h * 2 * BT_HK;
           tmem_st_x16(taddr, hi);
           tmem_st_x16(taddr + BT_HK, lo);
-          if (j == cpt - 1 && h == 1) {
-            // sN2 of the previous tile was consumed before facc_empty, which MMA1 waited for before this tile's MMAs
-            sN2[m] = n2_of(n2);
-          }
+          // sN2[i & 1] was last read by the derivative warps of tile i-2, which finished before MMA2 of tile i-2, which
+          // MMA1 of this tile waited for (g_empty) before consuming the A buffers this loop has been refilling
+          if (j == cpt - 1 && h == 1) sN2[(i & 1) * BT_BM + m] = n2_of(n2);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&a_full[h]);
         }
         if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == NST) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp >= 8 && warp < 12) {
@@ -247,95 +259,89 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
     const int wq = warp & 3, m = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
     const HeadConsts hc = a.hc;
+    const int O = a.O;
     for (int i = 0; i < my_tiles; ++i) {
+      const int b = i & 1;
       const int tile = blockIdx.x + i * gridDim.x;
       const int n = tile / a.tiles_per_img;
       const int p = (tile - n * a.tiles_per_img) * BT_BM + m;
       const bool live = (p < HW);
-      mbar_wait(facc_full, (uint32_t)i & 1u);
-      tc_fence_after();
-      const float n2 = sN2[m];
-      float S[OP], T[OP];
-      {
-        float buf[2 * OP], cor[2 * OP];
-        const uint32_t taddr = tmem_base + lane_addr + BT_FACC_COL;
+      const float* dl = a.dlogits + (size_t)n * O * HW + p;
+      float* gpl = a.G + (size_t)n * 2 * OP * HW + p;
+      float Gn[4];   // upstream gradients of the next class group (in flight under the math of the current one)
 #pragma unroll
-        for (int c8 = 0; c8 < (2 * OP) / 8; ++c8) {
-          tmem_ld_x8(taddr + c8 * 8, *reinterpret_cast<float(*)[8]>(&buf[c8 * 8]));
-          tmem_ld_x8(taddr + NP + c8 * 8, *reinterpret_cast<float(*)[8]>(&cor[c8 * 8]));
+      for (int e = 0; e < 4; ++e) Gn[e] = (live && e < O) ? __ldg(dl + (size_t)e * HW) : 0.f;
+      mbar_wait(&facc_full[b], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const PixelScalarGrads ps = tangent_scalar_grads(sN2[b * BT_BM + m], hc);
+      const uint32_t fg = tmem_base + lane_addr + BT_FG_COL + b * 2 * NP;   // main | correction -> G hi | G lo
+      float g_gamma = 0.f, g_t2 = 0.f, g_om = 0.f;
+#pragma unroll 1
+      for (int k0 = 0; k0 < OP; k0 += 4) {
+        float Sm[4], Sc[4], Tm[4], Tc[4], Gc[4];
+        tmem_ld_x4(fg + k0, Sm);
+        tmem_ld_x4(fg + OP + k0, Tm);
+        tmem_ld_x4(fg + NP + k0, Sc);
+        tmem_ld_x4(fg + NP + OP + k0, Tc);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          Gc[e] = Gn[e];
+          const int kn = k0 + 4 + e;
+          Gn[e] = (live && kn < O) ? __ldg(dl + (size_t)kn * HW) : 0.f;
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float gS[4], gT[4];
 #pragma unroll
-        for (int k = 0; k < OP; ++k) { S[k] = buf[k] + cor[k]; T[k] = buf[OP + k] + cor[OP + k]; }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(facc_empty);
-
-      const PixelScalarGrads ps = tangent_scalar_grads(n2, hc);
-      float g_gamma = 0.f, g_t2 = 0.f, g_om = 0.f;
-      float gS[OP], gT[OP];
+        for (int e = 0; e < 4; ++e) {
+          const int k = k0 + e;
+          float d_pp = 0.f, d_an = 0.f, d_pa = 0.f;
+          gS[e] = gT[e] = 0.f;
+          if (k < O) {   // warp-uniform
+            const float4 cl = reinterpret_cast<const float4*>(sCls)[k];
+            mlr_logit_grad(Gc[e], Sm[e] + Sc[e], Tm[e] + Tc[e], ps, cl.x, cl.y, cl.z, cl.w, hc, gS[e], gT[e], g_gamma, g_t2,
+                           g_om, d_pp, d_an, d_pa);
+            // class scalars: fixed-order warp reduction into this warp's slot
 #pragma unroll
-      for (int k = 0; k < OP; ++k) {
-        gS[k] = gT[k] = 0.f;
-        float d_pp = 0.f, d_an = 0.f, d_pa = 0.f;
-        if (k < a.O) {
-          const float G = live ? __ldg(a.dlogits + ((size_t)n * a.O + k) * HW + p) : 0.f;
-          const float4 cl = reinterpret_cast<const float4*>(sCls)[k];
-          mlr_logit_grad(G, S[k], T[k], ps, cl.x, cl.y, cl.z, cl.w, hc, gS[k], gT[k], g_gamma, g_t2, g_om, d_pp, d_an, d_pa);
-        }
-        // class scalars: fixed-order warp reduction into this warp's slot
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          d_pp += __shfl_xor_sync(0xffffffffu, d_pp, o);
-          d_an += __shfl_xor_sync(0xffffffffu, d_an, o);
-          d_pa += __shfl_xor_sync(0xffffffffu, d_pa, o);
-        }
-        if (lane == 0) {
-          sRed[(wq * 3 + 0) * OP + k] += d_pp;
-          sRed[(wq * 3 + 1) * OP + k] += d_an;
-          sRed[(wq * 3 + 2) * OP + k] += d_pa;
-        }
-      }
-      const float alpha = 2.f * (g_gamma * ps.dgam + g_t2 * ps.dt2 + g_om * ps.dom);
-      // fp32 G planes for the weight-gradient kernel
-      if (live) {
-#pragma unroll
-        for (int k = 0; k < OP; ++k) {
-          a.G[((size_t)n * 2 * OP + k) * HW + p] = gS[k];
-          a.G[((size_t)n * 2 * OP + OP + k) * HW + p] = gT[k];
-        }
-      }
-      // G -> TMEM (hi, lo), columns n = [gS (OP) | gT (OP) | zeros up to NP]
-      mbar_wait(g_empty, ((uint32_t)i & 1u) ^ 1u);   // MMA2 of the previous tile has consumed G
-      mbar_wait(d2_empty, ((uint32_t)i & 1u) ^ 1u);  // ... and the output warps are done with sAlpha
-      tc_fence_after();
-      {
-        float gv[NP];
-#pragma unroll
-        for (int k = 0; k < NP; ++k) gv[k] = 0.f;   // columns >= 2*OP multiply zero parameter rows but must be finite
-#pragma unroll
-        for (int k = 0; k < OP; ++k) { gv[k] = gS[k]; gv[OP + k] = gT[k]; }
-        const uint32_t taddr = tmem_base + lane_addr + G_COL;
-#pragma unroll
-        for (int c16 = 0; c16 < NP / 16; ++c16) {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float v = gv[c16 * 16 + e];
-            const uint32_t hb = cvt_rna_tf32(v);
-            hi[e] = hb;
-            lo[e] = cvt_rna_tf32(v - __uint_as_float(hb));
+            for (int o = 16; o > 0; o >>= 1) {
+              d_pp += __shfl_xor_sync(0xffffffffu, d_pp, o);
+              d_an += __shfl_xor_sync(0xffffffffu, d_an, o);
+              d_pa += __shfl_xor_sync(0xffffffffu, d_pa, o);
+            }
+            if (lane == 0) {
+              sRed[(wq * 3 + 0) * OP + k] += d_pp;
+              sRed[(wq * 3 + 1) * OP + k] += d_an;
+              sRed[(wq * 3 + 2) * OP + k] += d_pa;
+            }
           }
-          tmem_st_x16(taddr + c16 * 16, hi);
-          tmem_st_x16(taddr + NP + c16 * 16, lo);
         }
+        // fp32 G planes for the weight-gradient kernel
+        if (live) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            gpl[(size_t)(k0 + e) * HW] = gS[e];
+            gpl[(size_t)(OP + k0 + e) * HW] = gT[e];
+          }
+        }
+        // G -> TMEM in place of the S, T it was derived from: hi over the main columns, lo over the correction columns
+        uint32_t sh[4], sl[4], th[4], tl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sh[e] = cvt_rna_tf32(gS[e]);
+          sl[e] = __float_as_uint(gS[e] - __uint_as_float(sh[e]));
+          th[e] = cvt_rna_tf32(gT[e]);
+          tl[e] = __float_as_uint(gT[e] - __uint_as_float(th[e]));
+        }
+        tmem_st_x4(fg + k0, sh);
+        tmem_st_x4(fg + OP + k0, th);
+        tmem_st_x4(fg + NP + k0, sl);
+        tmem_st_x4(fg + NP + OP + k0, tl);
       }
-      sAlpha[m] = alpha;
+      mbar_wait(&alpha_free[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);   // the output warps have read alpha of tile i-2
+      sAlpha[b * BT_BM + m] = 2.f * (g_gamma * ps.dgam + g_t2 * ps.dt2 + g_om * ps.dom);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(g_full);
+      if (lane == 0) mbar_arrive(&g_full[b]);
     }
   } else if (warp >= 12) {
     // =================== output warps (thread = pixel): du = D2 + alpha * u ===================
@@ -348,15 +354,25 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
       const bool live = (p < HW);
       const float* ubase = a.feat + (size_t)n * C * HW + p;
       float* dbase = a.dfeat + (size_t)n * C * HW + p;
+      // the features of the first channel group do not depend on D2: request them before waiting for the MMA, and keep
+      // one group (32 channels) of loads in flight under the TMEM read / store of the previous one
+      float un[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) un[e] = live ? __ldcs(ubase + (size_t)e * HW) : 0.f;
       mbar_wait(d2_full, (uint32_t)i & 1u);
       tc_fence_after();
-      const float alpha = sAlpha[m];
+      const float alpha = sAlpha[(i & 1) * BT_BM + m];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&alpha_free[i & 1]);
       for (int c0 = 0; c0 < C; c0 += 32) {
-        float d[32];
+        float d[32], u[32];
         tmem_ld_x32(tmem_base + lane_addr + BT_D2_COL + c0, d);
-        float u[32];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) u[e] = live ? __ldg(ubase + (size_t)(c0 + e) * HW) : 0.f;
+        for (int e = 0; e < 32; ++e) u[e] = un[e];
+        if (c0 + 32 < C) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) un[e] = live ? __ldcs(ubase + (size_t)(c0 + 32 + e) * HW) : 0.f;
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (live) {
 #pragma unroll
@@ -382,13 +398,13 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
   }
 }
 
-// transposed parameter planes for MMA2: [2 (hi,lo)][NP/4][C][4], value(c, n) = Wt[c][n] of the CUDA-core pack (0 for n >= 2*OP)
-__global__ void head_pack_bwd_planes_kernel(const float* __restrict__ std_pack, float* __restrict__ w2, int C, int OP, int NP) {
-  const int KP = 2 * OP, total = NP * C;
+// transposed parameter planes for MMA2: [2 (hi,lo)][NR/4][C][4], NR = 2*OP, value(c, n) = Wt[c][n] of the CUDA-core pack
+__global__ void head_pack_bwd_planes_kernel(const float* __restrict__ std_pack, float* __restrict__ w2, int C, int OP) {
+  const int NR = 2 * OP, total = NR * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int n4 = i / (C * 4), rem = i - n4 * C * 4;
     const int ch = rem >> 2, n = n4 * 4 + (rem & 3);
-    const float w = (n < KP) ? std_pack[(size_t)ch * KP + n] : 0.f;
+    const float w = std_pack[(size_t)ch * NR + n];
     const uint32_t h = cvt_rna_tf32(w);
     w2[i] = __uint_as_float(h);
     w2[(size_t)total + i] = __uint_as_float(cvt_rna_tf32(w - __uint_as_float(h)));
@@ -397,9 +413,9 @@ __global__ void head_pack_bwd_planes_kernel(const float* __restrict__ std_pack, 
 
 // ---- host side -----------------------------------------------------------------------------------------
 bool head_bwd_tc_supported(int C, int O, int H, int W, const void* feat, const void* dfeat) {
-  if (C % BT_BK != 0 || C > 256 || C < BT_BK || C % 16 != 0) return false;
+  if (C % BT_BK != 0 || C > 256 || C < 2 * BT_BK) return false;  // >= 2 pipeline stages per tile (sN2 hand-over, see converters)
   const int NP = round_up(2 * head_op_pad(O), 16);
-  if (BT_FACC_COL + 4 * NP > BT_D2_COL) return false;  // O <= 24
+  if (BT_FG_COL + 4 * NP > BT_D2_COL) return false;  // O <= 24
   if (((long long)H * W) % 4 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(feat) & 15) != 0) return false;
   const BtSmem L = bt_smem_layout(NP, head_op_pad(O), C);
@@ -430,7 +446,7 @@ int head_bwd_tc_launch(const float* feat, const float* dlogits, float* dfeat, fl
     return HALO_ERR_CUDA;
   }
   const int OP = head_op_pad(O), NP = round_up(2 * OP, 16), HW = H * W;
-  head_pack_bwd_planes_kernel<<<(NP * C + 255) / 256, 256, 0, st>>>(std_pack, w2, C, OP, NP);
+  head_pack_bwd_planes_kernel<<<(2 * OP * C + 255) / 256, 256, 0, st>>>(std_pack, w2, C, OP);
   {
     int rc = launch_status("head_pack_bwd_planes_kernel");
     if (rc) return rc;

@@ -56,7 +56,8 @@ struct TcSmemLayout {
 };
 __host__ __device__ inline TcSmemLayout tc_smem_layout(int NP, int OP, int C) {
   TcSmemLayout L;
-  L.w_bytes = (size_t)2 * NP * C * 4;
+  (void)NP;
+  L.w_bytes = (size_t)2 * (2 * OP) * C * 4;  // only the 2*OP real rows are stored (see head_pack_tc_kernel)
   L.ring_off = (L.w_bytes + 1023) / 1024 * 1024;
   L.bar_off = L.ring_off + (size_t)TC_STAGES * TC_STAGE_FLOATS * 4;
   const int nbars = 2 * TC_STAGES + TC_NWG * 2 * 2 + TC_NWG * 2;
@@ -83,7 +84,8 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
   extern __shared__ __align__(1024) unsigned char smem[];
   const int C = a.C;
   const TcSmemLayout L = tc_smem_layout(NP, OP, C);
-  float* sW = reinterpret_cast<float*>(smem);  // [2][C/4][NP][4]: hi plane then lo plane
+  constexpr int NR = 2 * OP;                   // stored rows of the B operand; the MMA's rows NR..NP-1 alias the next K slice
+  float* sW = reinterpret_cast<float*>(smem);  // [2][C/4][NR][4]: hi plane then lo plane
   float* ring = reinterpret_cast<float*>(smem + L.ring_off);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* full = bars;
@@ -100,11 +102,11 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
 
   // ---- one-time setup ----
   {
-    const int n4 = 2 * NP * C / 4;
+    const int n4 = 2 * NR * C / 4;
     const float4* src = reinterpret_cast<const float4*>(wtc);
     float4* dst = reinterpret_cast<float4*>(sW);
     for (int i = threadIdx.x; i < n4; i += TC_THREADS) dst[i] = src[i];
-    const float* csrc = wtc + (size_t)2 * NP * C;  // [4][OP] -> per-class float4 {pp, an, pa, Bk}
+    const float* csrc = wtc + (size_t)2 * NR * C;  // [4][OP] -> per-class float4 {pp, an, pa, Bk}
     for (int i = threadIdx.x; i < 4 * OP; i += TC_THREADS) sCls[(i % OP) * 4 + i / OP] = csrc[i];
   }
   if (threadIdx.x == 0) {
@@ -175,8 +177,8 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     if (lane == 0) {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N=NP, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + (size_t)NP * C);
-      const uint32_t lbo = NP * 16, sbo = 128;
+      const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + (size_t)NR * C);
+      const uint32_t lbo = NR * 16, sbo = 128;
       const uint32_t d_corr = tmem_base + TC_ACC_COL0 + (g * NACC + NMAIN) * NP;
       for (int i = g; i < my_tiles; i += TC_NWG) {
         const int it = i / TC_NWG;
@@ -334,17 +336,20 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
 
 // ---- class parameters in the tensor-core operand layout ---------------------------------------------------
 // in : std pack  Wt[CPAD][2*OP] + cls[4][OP]     (head_pack_kernel)
-// out: W planes  [2 (hi,lo)][C/4][NP][4] fp32 with TF32-representable values (round-to-nearest split),
-//      followed by cls[4][OP].  Row n of the B operand: n < OP -> -P_n ; OP <= n < 2*OP -> a_hat_{n-OP} ; rest 0.
-__global__ void head_pack_tc_kernel(const float* __restrict__ std_pack, float* __restrict__ wtc, int C, int CPAD, int OP, int NP) {
-  const int KP = 2 * OP;
-  const int total = NP * C;
+// out: W planes  [2 (hi,lo)][C/4][NR][4] fp32 with TF32-representable values (round-to-nearest split), NR = 2*OP,
+//      followed by cls[4][OP].  Row n of the B operand: n < OP -> -P_n ; OP <= n < 2*OP -> a_hat_{n-OP}.
+//      The MMA runs with N = NP (NR rounded up to 16): its rows NR..NP-1 fall on the first rows of the next K slice
+//      (finite values) and only feed accumulator columns that nobody reads -- a column of D depends on its own row
+//      of B alone -- so the padding rows are not stored (16 KB of shared memory at C=256, O=19).
+__global__ void head_pack_tc_kernel(const float* __restrict__ std_pack, float* __restrict__ wtc, int C, int CPAD, int OP) {
+  const int NR = 2 * OP;
+  const int total = NR * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int k4 = i / (NP * 4);
-    const int rem = i - k4 * NP * 4;
+    const int k4 = i / (NR * 4);
+    const int rem = i - k4 * NR * 4;
     const int nrow = rem >> 2, kk = rem & 3;
     const int ch = k4 * 4 + kk;
-    const float w = (nrow < KP) ? std_pack[(size_t)ch * KP + nrow] : 0.f;
+    const float w = std_pack[(size_t)ch * NR + nrow];
     uint32_t h, l;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(w));
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(w - __uint_as_float(h)));
@@ -352,7 +357,7 @@ __global__ void head_pack_tc_kernel(const float* __restrict__ std_pack, float* _
     wtc[(size_t)total + i] = __uint_as_float(l);
   }
   if (blockIdx.x == 0) {
-    for (int i = threadIdx.x; i < 4 * OP; i += blockDim.x) wtc[(size_t)2 * total + i] = std_pack[(size_t)CPAD * KP + i];
+    for (int i = threadIdx.x; i < 4 * OP; i += blockDim.x) wtc[(size_t)2 * total + i] = std_pack[(size_t)CPAD * NR + i];
   }
 }
 
@@ -374,8 +379,8 @@ bool head_tc_supported(int feat_kind, int C, int O, int H, int W, const void* fe
 }
 
 int head_pack_tc_launch(const float* std_pack, float* wtc, int C, int CPAD, int O, cudaStream_t st) {
-  const int OP = head_op_pad(O), NP = head_tc_np(O);
-  head_pack_tc_kernel<<<(NP * C + 255) / 256, 256, 0, st>>>(std_pack, wtc, C, CPAD, OP, NP);
+  const int OP = head_op_pad(O);
+  head_pack_tc_kernel<<<(2 * OP * C + 255) / 256, 256, 0, st>>>(std_pack, wtc, C, CPAD, OP);
   return launch_status("head_pack_tc_kernel");
 }
 
@@ -394,7 +399,7 @@ static int launch_tc(const CUtensorMap& tmap, const HeadArgs& a, const float* wt
 
 int head_fwd_tc_launch(HeadArgs a, const float* std_pack, float* wtc, cudaStream_t st) {
   const int OP = head_op_pad(a.O), NP = head_tc_np(a.O);
-  head_pack_tc_kernel<<<(NP * a.C + 255) / 256, 256, 0, st>>>(std_pack, wtc, a.C, a.CPAD, OP, NP);
+  head_pack_tc_kernel<<<(2 * OP * a.C + 255) / 256, 256, 0, st>>>(std_pack, wtc, a.C, a.CPAD, OP);
   int rc = launch_status("head_pack_tc_kernel");
   if (rc) return rc;
   EncodeTiledFn enc = get_encode_fn();
