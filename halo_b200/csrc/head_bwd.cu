@@ -473,15 +473,22 @@ extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, 
     cls_grid = head_bwd_tc_grid(N, HW);
     rc = head_bwd_tc_launch(feat, dlogits, dfeat, G, cls_part, wpack, wtc, w2, c, N, C, O, H, W, cls_grid, st);
     if (rc) return rc;
-    switch (OP) {
-      case 4: head_bwd_dw_kernel<4><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
-      case 8: head_bwd_dw_kernel<8><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
-      case 12: head_bwd_dw_kernel<12><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
-      case 16: head_bwd_dw_kernel<16><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
-      case 20: head_bwd_dw_kernel<20><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
-      default: head_bwd_dw_kernel<24><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, (long long)N * ((HW + DW_PX - 1) / DW_PX)); break;
+    const char* force_dw = getenv("HALO_BWD_DW_CUDA_CORE");  // parity tests pin the fp32 CUDA-core weight-gradient GEMM
+    if (!(force_dw && force_dw[0] == '1') && head_bwd_dw_tc_supported(C, O, H, W, feat, G)) {
+      dw_grid = head_bwd_dw_tc_grid(N, HW);
+      rc = head_bwd_dw_tc_launch(feat, G, dw_part, N, C, O, H, W, CP, dw_grid, st);
+    } else {
+      const long long units = (long long)N * ((HW + DW_PX - 1) / DW_PX);
+      switch (OP) {
+        case 4: head_bwd_dw_kernel<4><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+        case 8: head_bwd_dw_kernel<8><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+        case 12: head_bwd_dw_kernel<12><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+        case 16: head_bwd_dw_kernel<16><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+        case 20: head_bwd_dw_kernel<20><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+        default: head_bwd_dw_kernel<24><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+      }
+      rc = launch_status("head_bwd_dw_kernel");
     }
-    rc = launch_status("head_bwd_dw_kernel");
   } else {
     switch (OP) {
       case 4: rc = launch_bwd<4>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;

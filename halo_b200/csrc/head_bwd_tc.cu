@@ -354,29 +354,41 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
       const bool live = (p < HW);
       const float* ubase = a.feat + (size_t)n * C * HW + p;
       float* dbase = a.dfeat + (size_t)n * C * HW + p;
-      // the features of the first channel group do not depend on D2: request them before waiting for the MMA, and keep
-      // one group (32 channels) of loads in flight under the TMEM read / store of the previous one
-      float un[32];
+      // The features do not depend on D2: the first two channel groups (2 x 32 loads per thread) are requested before
+      // waiting for the MMA, and two groups stay in flight under the TMEM read / store of the current one.  The re-read
+      // misses L2 two times out of three (profiles/r1_k4.md), so this stage lives on memory-level parallelism.
+      float ua[32], ub[32];
 #pragma unroll
-      for (int e = 0; e < 32; ++e) un[e] = live ? __ldcs(ubase + (size_t)e * HW) : 0.f;
+      for (int e = 0; e < 32; ++e) ua[e] = live ? __ldcs(ubase + (size_t)e * HW) : 0.f;
+#pragma unroll
+      for (int e = 0; e < 32; ++e) ub[e] = live ? __ldcs(ubase + (size_t)(32 + e) * HW) : 0.f;
       mbar_wait(d2_full, (uint32_t)i & 1u);
       tc_fence_after();
       const float alpha = sAlpha[(i & 1) * BT_BM + m];
       __syncwarp();
       if (lane == 0) mbar_arrive(&alpha_free[i & 1]);
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        float d[32], u[32];
+      for (int c0 = 0; c0 < C; c0 += 64) {
+        float d[32];
         tmem_ld_x32(tmem_base + lane_addr + BT_D2_COL + c0, d);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) u[e] = un[e];
-        if (c0 + 32 < C) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) un[e] = live ? __ldcs(ubase + (size_t)(c0 + 32 + e) * HW) : 0.f;
-        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (live) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) __stcs(dbase + (size_t)(c0 + e) * HW, fmaf(alpha, u[e], d[e]));
+        for (int e = 0; e < 32; ++e) {
+          if (live) __stcs(dbase + (size_t)(c0 + e) * HW, fmaf(alpha, ua[e], d[e]));
+        }
+        if (c0 + 64 < C) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) ua[e] = live ? __ldcs(ubase + (size_t)(c0 + 64 + e) * HW) : 0.f;
+        }
+        if (c0 + 32 >= C) break;   // C = 96, 160, 224: an odd number of channel groups
+        tmem_ld_x32(tmem_base + lane_addr + BT_D2_COL + c0 + 32, d);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          if (live) __stcs(dbase + (size_t)(c0 + 32 + e) * HW, fmaf(alpha, ub[e], d[e]));
+        }
+        if (c0 + 96 < C) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) ub[e] = live ? __ldcs(ubase + (size_t)(c0 + 96 + e) * HW) : 0.f;
         }
       }
       tc_fence_before();

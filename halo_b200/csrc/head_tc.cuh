@@ -20,4 +20,10 @@ int head_bwd_tc_grid(int N, int HW);
 int head_bwd_tc_launch(const float* feat, const float* dlogits, float* dfeat, float* G, float* cls_part, const float* std_pack,
                        const float* wtc, float* w2, float c, int N, int C, int O, int H, int W, int grid, cudaStream_t st);
 
+// tensor-core weight gradient dW = G^T.U (head_bwd_dw_tc.cu)
+bool head_bwd_dw_tc_supported(int C, int O, int H, int W, const void* feat, const void* G);
+int head_bwd_dw_tc_grid(int N, int HW);
+int head_bwd_dw_tc_launch(const float* feat, const float* G, float* dw_part, int N, int C, int O, int H, int W, int CP, int grid,
+                          cudaStream_t st);
+
 }  // namespace halo

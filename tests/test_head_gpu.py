@@ -163,7 +163,12 @@ def test_backward_tensor_core_pixel_pass(shape, monkeypatch):
     du_ref, dP_ref, dA_ref = ohead.head_grads(u, P, A, dl, 1.0)
     args = (u.to(DEV), P.to(DEV), A.to(DEV), 1.0, dl.to(DEV))
     monkeypatch.delenv("HALO_BWD_CUDA_CORE", raising=False)
-    du, dP, dA = halo_b200.head_backward(*args)
+    monkeypatch.delenv("HALO_BWD_DW_CUDA_CORE", raising=False)
+    du, dP, dA = halo_b200.head_backward(*args)              # tcgen05 pixel pass + tcgen05 weight gradient (C = 128, 256)
+    monkeypatch.setenv("HALO_BWD_DW_CUDA_CORE", "1")
+    _, dP_mix, dA_mix = halo_b200.head_backward(*args)       # tcgen05 pixel pass + fp32 CUDA-core weight gradient
+    assert rel_err(dP_mix, dP_ref) <= 1e-4 and rel_err(dA_mix, dA_ref) <= 1e-4
+    assert rel_err(dP, dP_mix) <= 2e-5 and rel_err(dA, dA_mix) <= 2e-5
     monkeypatch.setenv("HALO_BWD_CUDA_CORE", "1")
     du_cc, dP_cc, dA_cc = halo_b200.head_backward(*args)
     # pixels sitting on the MLR projection switch (derivative discontinuity) may take either branch in fp32:
@@ -208,3 +213,24 @@ def test_backward_is_deterministic():
     b = halo_b200.head_backward(u, P.to(DEV), A.to(DEV), 1.0, dl)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize("shape", [(19, 256, 640, 1280, 2), (16, 128, 512, 1024, 3)])
+def test_backward_full_size_tensor_core_vs_cuda_core(shape, monkeypatch):
+    """BASELINE configs[4] geometry: many tiles per CTA, several accumulator drains of the weight-gradient kernel, the
+    double-buffered TMEM regions wrapping hundreds of times.  The fp64 oracle takes minutes at this size, so the two
+    independent GPU paths (tcgen05 vs fp32 CUDA cores, each pinned to the oracle at small sizes) are compared."""
+    O, C, H, W, N = shape
+    P, A = synth.head_params(O, C, seed=2, device=DEV)
+    u = torch.stack([synth.image_features(i, C, H, W, device=DEV) for i in range(N)])
+    dl = torch.randn((N, O, H, W), device=DEV, generator=torch.Generator(device=DEV).manual_seed(5)) * 1e-3
+    monkeypatch.delenv("HALO_BWD_CUDA_CORE", raising=False)
+    monkeypatch.delenv("HALO_BWD_DW_CUDA_CORE", raising=False)
+    du, dP, dA = halo_b200.head_backward(u, P, A, 1.0, dl)
+    du2, dP2, dA2 = halo_b200.head_backward(u, P, A, 1.0, dl)
+    assert torch.equal(du, du2) and torch.equal(dP, dP2) and torch.equal(dA, dA2)   # fixed-order reductions
+    monkeypatch.setenv("HALO_BWD_CUDA_CORE", "1")
+    du_cc, dP_cc, dA_cc = halo_b200.head_backward(u, P, A, 1.0, dl)
+    assert rel_err(du, du_cc) <= 1e-4
+    assert rel_err(dP, dP_cc) <= 1e-4
+    assert rel_err(dA, dA_cc) <= 1e-4
