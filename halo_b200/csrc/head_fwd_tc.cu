@@ -42,9 +42,15 @@ constexpr int TC_STAGE_FLOATS = TC_BK * TC_BM;
 constexpr int TC_NWG = 2;       // converter warpgroups (each owns a TMA ring, an MMA issuer, A buffers and accumulators)
 constexpr int TC_THREADS = 128 + 128 * TC_NWG + 128;  // control warps + converters + one epilogue warpgroup
 constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_HK = 16;       // channels per A-operand half-buffer (two per pipeline stage)
-constexpr int TC_ACOLS = 2 * TC_HK;                 // per A half-buffer: 16 hi + 16 lo columns
-constexpr int TC_ACC_COL0 = TC_NWG * 2 * TC_ACOLS;  // = 128: accumulators start after the A buffers
+#ifndef HALO_TC_HK
+#define HALO_TC_HK 16
+#endif
+// channels per A-operand buffer (one converter -> MMA hand-over).  8 (four buffers per warpgroup, finer hand-overs) was
+// measured slower than 16 (two buffers): 4 080 vs 4 250 GB/s sustained -- the barrier traffic costs more than the depth wins.
+constexpr int TC_HK = HALO_TC_HK;
+constexpr int TC_NBUF = TC_BK / TC_HK;              // A buffers per warpgroup = hand-overs per pipeline stage
+constexpr int TC_ACOLS = 2 * TC_HK;                 // per A buffer: TC_HK hi + TC_HK lo columns
+constexpr int TC_ACC_COL0 = TC_NWG * TC_NBUF * TC_ACOLS;  // = 128: accumulators start after the A buffers
 constexpr int TC_NACC_MAX = 4;  // partial accumulators per tile (shortens the in-TMEM accumulation chains)
 
 // i-th tile of CTA b (G CTAs): the NWG warpgroups of a CTA take ADJACENT 128-pixel tiles (2b, 2b+1, then +2G ...), so a
@@ -60,7 +66,7 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int NP, int OP, int C) {
   L.w_bytes = (size_t)2 * (2 * OP) * C * 4;  // only the 2*OP real rows are stored (see head_pack_tc_kernel)
   L.ring_off = (L.w_bytes + 1023) / 1024 * 1024;
   L.bar_off = L.ring_off + (size_t)TC_STAGES * TC_STAGE_FLOATS * 4;
-  const int nbars = 2 * TC_STAGES + TC_NWG * 2 * 2 + TC_NWG * 2;
+  const int nbars = 2 * TC_STAGES + TC_NWG * TC_NBUF * 2 + TC_NWG * 2;
   L.tmem_off = L.bar_off + (size_t)nbars * 8;
   L.cls_off = (L.tmem_off + 16 + 15) / 16 * 16;
   L.n2_off = L.cls_off + (size_t)4 * OP * 4;
@@ -91,8 +97,8 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
   uint64_t* full = bars;
   uint64_t* empty = bars + TC_STAGES;
   uint64_t* a_full = bars + 2 * TC_STAGES;               // [NWG][2]
-  uint64_t* a_empty = a_full + TC_NWG * 2;               // [NWG][2]
-  uint64_t* acc_full = a_empty + TC_NWG * 2;             // [NWG]
+  uint64_t* a_empty = a_full + TC_NWG * TC_NBUF;         // [NWG][NBUF]
+  uint64_t* acc_full = a_empty + TC_NWG * TC_NBUF;       // [NWG]
   uint64_t* acc_empty = acc_full + TC_NWG;               // [NWG]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
   float* sCls = reinterpret_cast<float*>(smem + L.cls_off);
@@ -114,7 +120,7 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 4);     // one elected lane per converter warp
     }
-    for (int i = 0; i < TC_NWG * 2; ++i) {
+    for (int i = 0; i < TC_NWG * TC_NBUF; ++i) {
       mbar_init(&a_full[i], 4);
       mbar_init(&a_empty[i], 1);   // tcgen05.commit
     }
@@ -188,10 +194,10 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
           const int ca = it * cpt + j;                      // stage counter of this warpgroup
           const uint32_t d_main = tmem_base + TC_ACC_COL0 + (g * NACC + (j % NMAIN)) * NP;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            mbar_wait(&a_full[g * 2 + h], (uint32_t)ca & 1u);
+          for (int h = 0; h < TC_NBUF; ++h) {
+            mbar_wait(&a_full[g * TC_NBUF + h], (uint32_t)ca & 1u);
             tc_fence_after();
-            const uint32_t a_col = tmem_base + (g * 2 + h) * TC_ACOLS;
+            const uint32_t a_col = tmem_base + (g * TC_NBUF + h) * TC_ACOLS;
 #pragma unroll
             for (int ks = 0; ks < TC_HK / 8; ++ks) {
               const uint32_t koff = (uint32_t)((j * TC_BK + h * TC_HK + ks * 8) / 4) * lbo;  // byte offset of the K-slice
@@ -202,7 +208,7 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
               tc_mma_tf32_ts(d_corr, a_col + TC_HK + ks * 8, b_hi, idesc, (j == 0 && first_k) ? 0u : 1u);  // lo . hi
               tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);                                 // hi . lo
             }
-            tc_commit(&a_empty[g * 2 + h]);
+            tc_commit(&a_empty[g * TC_NBUF + h]);
           }
         }
         tc_commit(&acc_full[g]);
@@ -224,21 +230,21 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
         mbar_wait(&full[s], (uint32_t)(ca / TC_WG_STAGES) & 1u);
         const float* src = ring + (size_t)s * TC_STAGE_FLOATS + m;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          mbar_wait(&a_empty[g * 2 + h], ((uint32_t)ca & 1u) ^ 1u);
+        for (int h = 0; h < TC_NBUF; ++h) {
+          mbar_wait(&a_empty[g * TC_NBUF + h], ((uint32_t)ca & 1u) ^ 1u);
           tc_fence_after();
           uint32_t hi[TC_HK], lo[TC_HK];
-          tc_split16(src + h * TC_HK * TC_BM, TC_BM, hi, lo, n2);
-          const uint32_t taddr = tmem_base + lane_addr + (g * 2 + h) * TC_ACOLS;
-          tmem_st_x16(taddr, hi);
-          tmem_st_x16(taddr + TC_HK, lo);
+          tc_split<TC_HK>(src + h * TC_HK * TC_BM, TC_BM, hi, lo, n2);
+          const uint32_t taddr = tmem_base + lane_addr + (g * TC_NBUF + h) * TC_ACOLS;
+          tmem_st(taddr, hi);
+          tmem_st(taddr + TC_HK, lo);
           // |u|^2 travels to the epilogue warpgroup through shared memory; it is published by the release of the
           // tile's last a_full arrival (-> MMA issuer -> tcgen05.commit -> acc_full acquire in the epilogue)
-          if (j == cpt - 1 && h == 1) sN2[g * TC_BM + m] = n2_of(n2);
+          if (j == cpt - 1 && h == TC_NBUF - 1) sN2[g * TC_BM + m] = n2_of(n2);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[g * 2 + h]);
+          if (lane == 0) mbar_arrive(&a_full[g * TC_NBUF + h]);
         }
         if (lane == 0) mbar_arrive(&empty[s]);
       }

@@ -87,10 +87,11 @@ __device__ __forceinline__ unsigned long long pack_f32x2(uint32_t a, uint32_t b)
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
   return r;
 }
-__device__ __forceinline__ void tc_split16(const float* __restrict__ src, int stride, uint32_t (&hi)[16], uint32_t (&lo)[16],
-                                           unsigned long long& n2acc) {
+template <int NK>
+__device__ __forceinline__ void tc_split(const float* __restrict__ src, int stride, uint32_t (&hi)[NK], uint32_t (&lo)[NK],
+                                         unsigned long long& n2acc) {
 #pragma unroll
-  for (int k = 0; k < 16; k += 2) {
+  for (int k = 0; k < NK; k += 2) {
     const uint32_t u0 = __float_as_uint(src[k * stride]), u1 = __float_as_uint(src[(k + 1) * stride]);
     const unsigned long long uu = pack_f32x2(u0, u1);
     asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(n2acc) : "l"(uu));
@@ -101,6 +102,10 @@ __device__ __forceinline__ void tc_split16(const float* __restrict__ src, int st
     hi[k + 1] = h1;
     asm("mov.b64 {%0, %1}, %2;" : "=r"(lo[k]), "=r"(lo[k + 1]) : "l"(ll));
   }
+}
+__device__ __forceinline__ void tc_split16(const float* __restrict__ src, int stride, uint32_t (&hi)[16], uint32_t (&lo)[16],
+                                           unsigned long long& n2acc) {
+  tc_split<16>(src, stride, hi, lo, n2acc);
 }
 __device__ __forceinline__ float n2_of(unsigned long long n2acc) {
   uint32_t a, b;
@@ -125,6 +130,13 @@ __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&v)[
       "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[8]) { tmem_st_x8(taddr, v); }
+__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st_x16(taddr, v); }
 __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
