@@ -322,6 +322,14 @@ def run_ours(args):
     if distributed:
         dist.barrier()
 
+    # ---- BASELINE.json configs[4] beside it (not the headline): fused head forward + backward, batch 8, fp32 ----
+    train = None
+    if rank == 0 and world == 1 and not args.no_train_step:
+        train = run_train_step(feat[:8], P, A, cfg.curvature, measured_peak_gbs()[0])
+        torch.cuda.empty_cache()
+    if distributed:
+        dist.barrier()
+
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
     e2e = run_e2e(args, cfg, P, A, dev, rank, world, distributed)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
@@ -332,12 +340,42 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(B), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": KERNELS_PER_STEP * args.steps, "picks_per_image": picks_ok,
+            "gpu_launches": KERNELS_PER_STEP * args.steps, "picks_per_image": picks_ok, "train_step": train,
             "round_seconds_at_this_rate": round(w["pool_images"] * H * W / (value * 1e6), 4),
         }
         print(json.dumps(line), flush=True)
     if distributed:
         dist.destroy_process_group()
+
+
+def run_train_step(feat8, P, A, c, peak):
+    """configs[4]: hyperbolic MLR head fused fwd+bwd on a resident batch (8 x 1280x640 x 256-d, 19 classes, fp32).
+    Algorithmic bytes 12*C + 8*O per pixel."""
+    import halo_b200
+
+    B, C, H, W = feat8.shape
+    O = P.shape[0]
+    dl = torch.randn((B, O, H, W), device=feat8.device, generator=torch.Generator(device=feat8.device).manual_seed(7)) * 1e-3
+
+    def step():
+        halo_b200.head_forward(feat8, P, A, c, want_logits=True)
+        return halo_b200.head_backward(feat8, P, A, c, dl)
+
+    for _ in range(3):
+        step()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    t0.record()
+    for _ in range(reps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / reps
+    px = B * H * W
+    alg = (12.0 * C + 8.0 * O) * px
+    return {"workload": "BASELINE.json configs[4]: head fwd+bwd, batch %d x %dx%d x %d-d, %d classes, fp32" % (B, W, H, C, O),
+            "ms_per_step": round(ms, 3), "Mpixel/s": round(px / ms / 1e3, 1), "algorithmic_GB_per_step": round(alg / 1e9, 2),
+            "GB/s": round(alg / ms / 1e6, 1), "frac_of_hbm_peak": round(alg / ms / 1e6 / peak, 4), "gpu_launches_per_step": 9}
 
 
 def run_e2e(args, cfg, P, A, dev, rank, world, distributed):
@@ -422,6 +460,7 @@ def main():
                     help="images resident per GPU per step (148 = one selection CTA per SM; 124 GB of features)")
     ap.add_argument("--e2e-batch", type=int, default=4, help="images per end-to-end step (pinned host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true", help="skip the configs[4] fwd+bwd side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
