@@ -5,6 +5,7 @@ Mirrors the reference's Python call surface for that path and nothing else:
     core/utils/hyperbolic.py       -> halo_b200.hyperbolic       (HyperMapper, HyperMLR)
     core/active/floating_region.py -> halo_b200.floating_region  (FloatingRegionScore)
     core/active/build.py           -> halo_b200.active           (select_pixels_to_label, RegionSelection)
+    mask / indicator files         -> halo_b200.maskio           (build.py:162-166, cityscapes.py:234,245-251)
 
 All arithmetic runs in hand-written CUDA behind the C ABI of include/halo_b200.h
 (halo_b200/libhalo_sm100.so); there is no CPU path and no fallback.
@@ -14,6 +15,7 @@ from .hyperbolic import HyperMapper, HyperMLR, PoincareEmbedding, head_forward, 
 from .floating_region import FloatingRegionScore  # noqa: F401
 from .active import RegionSelection, select_pixels_to_label, select_planes  # noqa: F401
 from .pool import AcquisitionConfig, acquire_batch, acquire_pool  # noqa: F401
+from .maskio import AsyncMaskWriter, read_indicator, read_mask  # noqa: F401
 from .dropin import install  # noqa: F401
 
 __version__ = "0.1.0"

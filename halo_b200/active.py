@@ -15,6 +15,7 @@ import torch.nn.functional as F
 from . import _native as nat
 from .floating_region import FloatingRegionScore
 from .hyperbolic import PoincareEmbedding
+from .maskio import AsyncMaskWriter
 
 
 def select_planes(score, active, selected, active_mask, gt, n_regions, active_radius, mask_radius, want_picks=False,
@@ -80,8 +81,6 @@ def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_
     Same loader item contract (core/datasets/cityscapes.py:274-286) and on-disk side effects.  The per-image
     body runs the CUDA path: classifier head (fused when the classifier was built with this package's
     HyperMapper/HyperMLR), FloatingRegionScore, select_pixels_to_label."""
-    from PIL import Image
-
     feature_extractor.eval()
     classifier.eval()
 
@@ -99,7 +98,11 @@ def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_
                        or purity_type in ["hyper", "radius", "euc_norm"]
                        or (uncertainty_type == "none" and cfg.MODEL.HYPER))
 
-    with torch.no_grad():
+    # PNG encoding + torch.save leave the loop: same files, written by a thread pool from pinned
+    # staging buffers; flushed before this function returns, as the caller expects (train_learners.py:318-322 reloads
+    # the dataset right after)
+    writer = AsyncMaskWriter(workers=int(getattr(cfg.ACTIVE, "IO_WORKERS", 4)))
+    with torch.no_grad(), writer:
         idx = 0
         for tgt_data in tgt_epoch_loader:
             tgt_input = tgt_data["img"].cuda(non_blocking=True)
@@ -138,8 +141,7 @@ def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_
                 score, active, selected, active_mask = select_pixels_to_label(
                     score, active_regions, active_radius, mask_radius, active, selected, active_mask, ground_truth)
 
-                Image.fromarray(to_np_array(active_mask)).save(path2mask[i])
-                torch.save({"active": active, "selected": selected}, path2indicator[i])
+                writer.write(active_mask, active, selected, path2mask[i], path2indicator[i])   # build.py:162-166
             idx += 1
 
     feature_extractor.train()
