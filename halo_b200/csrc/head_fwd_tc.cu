@@ -48,7 +48,11 @@ constexpr int TC_TMEM_COLS = 512;
 // channels per A-operand buffer (one converter -> MMA hand-over).  8 (four buffers per warpgroup, finer hand-overs) was
 // measured slower than 16 (two buffers): 4 080 vs 4 250 GB/s sustained -- the barrier traffic costs more than the depth wins.
 constexpr int TC_HK = HALO_TC_HK;
-constexpr int TC_NBUF = TC_BK / TC_HK;              // A buffers per warpgroup = hand-overs per pipeline stage
+constexpr int TC_NHAND = TC_BK / TC_HK;             // hand-overs per pipeline stage
+#ifndef HALO_TC_NBUF
+#define HALO_TC_NBUF (TC_BK / TC_HK)
+#endif
+constexpr int TC_NBUF = HALO_TC_NBUF;               // A buffers per warpgroup, used round-robin by hand-over
 constexpr int TC_ACOLS = 2 * TC_HK;                 // per A buffer: TC_HK hi + TC_HK lo columns
 constexpr int TC_ACC_COL0 = TC_NWG * TC_NBUF * TC_ACOLS;  // = 128: accumulators start after the A buffers
 constexpr int TC_NACC_MAX = 4;  // partial accumulators per tile (shortens the in-TMEM accumulation chains)
@@ -179,42 +183,49 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     // One issuing thread per pixel warpgroup, each strictly in order for ITS warpgroup: the two conversion
     // streams then overlap on the tensor pipe instead of being serialised behind a single in-order issuer
     // (tcgen05.commit tracks the MMAs of the executing thread only, and the two streams touch disjoint TMEM).
-    const int g = warp >> 1;
-    if (lane == 0) {
+    // The loop runs warp-wide (converged) and only the tcgen05 instructions are predicated on an elected lane; warp
+    // index and TMEM base go through a shuffle so that ptxas sees every MMA operand as warp-uniform.
+    const int g = __shfl_sync(0xffffffffu, warp >> 1, 0);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    {
       // instruction descriptor: D=f32, A=B=tf32, both K-major, N=NP, M=128
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + (size_t)NR * C);
+      const uint32_t w_hi = __shfl_sync(0xffffffffu, smem_u32(sW), 0), w_lo = w_hi + (uint32_t)NR * C * 4;
       const uint32_t lbo = NR * 16, sbo = 128;
-      const uint32_t d_corr = tmem_base + TC_ACC_COL0 + (g * NACC + NMAIN) * NP;
+      const uint32_t d_corr = tb + TC_ACC_COL0 + (g * NACC + NMAIN) * NP;
       for (int i = g; i < my_tiles; i += TC_NWG) {
         const int it = i / TC_NWG;
         mbar_wait(&acc_empty[g], ((uint32_t)it & 1u) ^ 1u);
         tc_fence_after();
         for (int j = 0; j < cpt; ++j) {
           const int ca = it * cpt + j;                      // stage counter of this warpgroup
-          const uint32_t d_main = tmem_base + TC_ACC_COL0 + (g * NACC + (j % NMAIN)) * NP;
+          const uint32_t d_main = tb + TC_ACC_COL0 + (g * NACC + (j % NMAIN)) * NP;
 #pragma unroll
-          for (int h = 0; h < TC_NBUF; ++h) {
-            mbar_wait(&a_full[g * TC_NBUF + h], (uint32_t)ca & 1u);
+          for (int h = 0; h < TC_NHAND; ++h) {
+            const int hc = ca * TC_NHAND + h, bf = hc % TC_NBUF;   // hand-over counter -> buffer, phase
+            mbar_wait(&a_full[g * TC_NBUF + bf], (uint32_t)(hc / TC_NBUF) & 1u);
             tc_fence_after();
-            const uint32_t a_col = tmem_base + (g * TC_NBUF + h) * TC_ACOLS;
+            const uint32_t a_col = tb + (g * TC_NBUF + bf) * TC_ACOLS;
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int ks = 0; ks < TC_HK / 8; ++ks) {
-              const uint32_t koff = (uint32_t)((j * TC_BK + h * TC_HK + ks * 8) / 4) * lbo;  // byte offset of the K-slice
-              const uint64_t b_hi = make_b_desc(w_hi + koff, lbo, sbo);
-              const uint64_t b_lo = make_b_desc(w_lo + koff, lbo, sbo);
-              const bool first_k = (h == 0 && ks == 0);
-              tc_mma_tf32_ts(d_main, a_col + ks * 8, b_hi, idesc, (j < NMAIN && first_k) ? 0u : 1u);   // hi . hi
-              tc_mma_tf32_ts(d_corr, a_col + TC_HK + ks * 8, b_hi, idesc, (j == 0 && first_k) ? 0u : 1u);  // lo . hi
-              tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);                                 // hi . lo
+              for (int ks = 0; ks < TC_HK / 8; ++ks) {
+                const uint32_t koff = (uint32_t)((j * TC_BK + h * TC_HK + ks * 8) / 4) * lbo;  // byte offset of the K-slice
+                const uint64_t b_hi = make_b_desc(w_hi + koff, lbo, sbo);
+                const uint64_t b_lo = make_b_desc(w_lo + koff, lbo, sbo);
+                const bool first_k = (h == 0 && ks == 0);
+                tc_mma_tf32_ts(d_main, a_col + ks * 8, b_hi, idesc, (j < NMAIN && first_k) ? 0u : 1u);   // hi . hi
+                tc_mma_tf32_ts(d_corr, a_col + TC_HK + ks * 8, b_hi, idesc, (j == 0 && first_k) ? 0u : 1u);  // lo . hi
+                tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);                                 // hi . lo
+              }
+              tc_commit(&a_empty[g * TC_NBUF + bf]);
             }
-            tc_commit(&a_empty[g * TC_NBUF + h]);
+            __syncwarp();
           }
         }
-        tc_commit(&acc_full[g]);
+        if (elect_one_sync()) tc_commit(&acc_full[g]);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp >= 4 && warp < 4 + 4 * TC_NWG) {
     // =================== converter warpgroups (thread = pixel = TMEM lane) ===================
     const int g = (warp - 4) >> 2;
@@ -230,21 +241,22 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
         mbar_wait(&full[s], (uint32_t)(ca / TC_WG_STAGES) & 1u);
         const float* src = ring + (size_t)s * TC_STAGE_FLOATS + m;
 #pragma unroll
-        for (int h = 0; h < TC_NBUF; ++h) {
-          mbar_wait(&a_empty[g * TC_NBUF + h], ((uint32_t)ca & 1u) ^ 1u);
+        for (int h = 0; h < TC_NHAND; ++h) {
+          const int hc = ca * TC_NHAND + h, bf = hc % TC_NBUF;
+          mbar_wait(&a_empty[g * TC_NBUF + bf], ((uint32_t)(hc / TC_NBUF) & 1u) ^ 1u);
           tc_fence_after();
           uint32_t hi[TC_HK], lo[TC_HK];
           tc_split<TC_HK>(src + h * TC_HK * TC_BM, TC_BM, hi, lo, n2);
-          const uint32_t taddr = tmem_base + lane_addr + (g * TC_NBUF + h) * TC_ACOLS;
+          const uint32_t taddr = tmem_base + lane_addr + (g * TC_NBUF + bf) * TC_ACOLS;
           tmem_st(taddr, hi);
           tmem_st(taddr + TC_HK, lo);
           // |u|^2 travels to the epilogue warpgroup through shared memory; it is published by the release of the
           // tile's last a_full arrival (-> MMA issuer -> tcgen05.commit -> acc_full acquire in the epilogue)
-          if (j == cpt - 1 && h == TC_NBUF - 1) sN2[g * TC_BM + m] = n2_of(n2);
+          if (j == cpt - 1 && h == TC_NHAND - 1) sN2[g * TC_BM + m] = n2_of(n2);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[g * TC_NBUF + h]);
+          if (lane == 0) mbar_arrive(&a_full[g * TC_NBUF + bf]);
         }
         if (lane == 0) mbar_arrive(&empty[s]);
       }
@@ -397,7 +409,7 @@ static int launch_tc(const CUtensorMap& tmap, const HeadArgs& a, const float* wt
   // as many main accumulators as TMEM allows next to the A buffers (at most one per pipeline stage of C=256)
   constexpr int FIT = (TC_TMEM_COLS - TC_ACC_COL0) / (TC_NWG * NP) - 1;
   constexpr int NMAIN = FIT > 8 ? 8 : FIT;
-  static_assert(NMAIN >= 2, "TMEM budget");
+  static_assert(NMAIN >= 1, "TMEM budget");
   HALO_CUDA(cudaFuncSetAttribute(head_fwd_tc_kernel<NP, OP, NMAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   head_fwd_tc_kernel<NP, OP, NMAIN><<<grid, TC_THREADS, smem, st>>>(tmap, a, wtc);
   return launch_status("head_fwd_tc_kernel");

@@ -61,6 +61,22 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One elected lane of a fully converged warp (the CUTLASS idiom).  The MMA-issuer warps run their loops warp-wide and
+// predicate only the tcgen05 instructions on this: under `if (lane == 0) { loop }` ptxas cannot prove the operands
+// uniform and wraps every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall (~13 instructions per MMA on one
+// lane: the issuer, not the tensor pipe, paced the converters -- profiles/r1_k1.md r1n).
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred));
+  return pred;
+}
 // D[tmem] (+)= A[tmem] . B[smem]     kind::tf32, cta_group::1
 __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
