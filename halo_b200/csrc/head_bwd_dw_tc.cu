@@ -99,7 +99,7 @@ head_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_c
 
   if (warp == 0) {
     // =================== TMA producer ===================
-    if (lane == 0) {
+    {
       int s = 0;
       uint32_t ph = 0;
       for (long long i = 0; i < my_units; ++i) {
@@ -108,21 +108,26 @@ head_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_c
         const int p0 = (int)(unit - (long long)n * a.units_per_img) * (DW_CHUNK * DW_UNIT_CHUNKS);
         for (int q = 0; q < DW_UNIT_CHUNKS; ++q) {
           mbar_wait(&empty[s], ph ^ 1u);
-          unsigned char* st = ring + (size_t)s * stage_bytes;
-          mbar_arrive_expect_tx(&full[s], (uint32_t)(nwg * DW_U_BOX_BYTES + NR * 128));
-          for (int g = 0; g < nwg; ++g) tma_load_2d(st + (size_t)g * DW_U_BOX_BYTES, &tmap_u, p0 + q * DW_CHUNK, n * a.C + g * 128, &full[s]);
-          tma_load_2d(st + (size_t)nwg * DW_U_BOX_BYTES, &tmap_g, p0 + q * DW_CHUNK, n * NR, &full[s]);
+          if (elect_one_sync()) {
+            unsigned char* st = ring + (size_t)s * stage_bytes;
+            mbar_arrive_expect_tx(&full[s], (uint32_t)(nwg * DW_U_BOX_BYTES + NR * 128));
+            for (int g = 0; g < nwg; ++g) tma_load_2d(st + (size_t)g * DW_U_BOX_BYTES, &tmap_u, p0 + q * DW_CHUNK, n * a.C + g * 128, &full[s]);
+            tma_load_2d(st + (size_t)nwg * DW_U_BOX_BYTES, &tmap_g, p0 + q * DW_CHUNK, n * NR, &full[s]);
+          }
+          __syncwarp();
           if (++s == NST) { s = 0; ph ^= 1u; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1 || warp == 3) {
     // =================== MMA issuers (warp 1: channels 0-127, warp 3: channels 128-255) ===================
-    const int g = warp >> 1;
-    if (lane == 0 && g < nwg) {
+    // warp-wide loop, tcgen05 instructions on an elected lane (see elect_one_sync in tc_common.cuh)
+    const int g = __shfl_sync(0xffffffffu, warp >> 1, 0);
+    if (g < nwg) {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t ring_u32 = __shfl_sync(0xffffffffu, smem_u32(ring), 0);
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t d_main = tmem_base + DW_ACC_COL + g * 2 * NP, d_corr = d_main + NP;
+      const uint32_t d_main = tb + DW_ACC_COL + g * 2 * NP, d_corr = d_main + NP;
       int s = 0;
       uint32_t ph = 0;
       long long ca = 0;
@@ -134,31 +139,36 @@ head_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_c
         }
         for (int q = 0; q < DW_UNIT_CHUNKS; ++q, ++ca) {
           mbar_wait(&g_ready[s], ph);
-          const uint32_t g_hi = smem_u32(ring + (size_t)s * stage_bytes + (size_t)nwg * DW_U_BOX_BYTES), g_lo = g_hi + (uint32_t)a.g_bytes;
+          const uint32_t g_hi = ring_u32 + (uint32_t)(s * stage_bytes) + (uint32_t)(nwg * DW_U_BOX_BYTES), g_lo = g_hi + (uint32_t)a.g_bytes;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             mbar_wait(&a_full[g * 2 + h], (uint32_t)ca & 1u);
             tc_fence_after();
-            const uint32_t a_col = tmem_base + DW_A_COL + (g * 2 + h) * 32;
+            const uint32_t a_col = tb + DW_A_COL + (g * 2 + h) * 32;
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint32_t koff = (uint32_t)(h * 16 + ks * 8) * 4;   // byte offset of the K slice inside the 128-byte rows
-              const uint64_t b_hi = make_b_desc_sw128(g_hi + koff);
-              const uint64_t b_lo = make_b_desc_sw128(g_lo + koff);
-              const uint32_t first = (chain_start && q == 0 && h == 0 && ks == 0) ? 0u : 1u;
-              tc_mma_tf32_ts(d_main, a_col + ks * 8, b_hi, idesc, first);
-              tc_mma_tf32_ts(d_corr, a_col + 16 + ks * 8, b_hi, idesc, first);
-              tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);
+              for (int ks = 0; ks < 2; ++ks) {
+                const uint32_t koff = (uint32_t)(h * 16 + ks * 8) * 4;   // byte offset of the K slice inside the 128-byte rows
+                const uint64_t b_hi = make_b_desc_sw128(g_hi + koff);
+                const uint64_t b_lo = make_b_desc_sw128(g_lo + koff);
+                const uint32_t first = (chain_start && q == 0 && h == 0 && ks == 0) ? 0u : 1u;
+                tc_mma_tf32_ts(d_main, a_col + ks * 8, b_hi, idesc, first);
+                tc_mma_tf32_ts(d_corr, a_col + 16 + ks * 8, b_hi, idesc, first);
+                tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);
+              }
+              tc_commit(&a_empty[g * 2 + h]);
+              if (h == 1) tc_commit(&empty[s]);
             }
-            tc_commit(&a_empty[g * 2 + h]);
+            __syncwarp();
           }
-          tc_commit(&empty[s]);
           if (++s == NST) { s = 0; ph ^= 1u; }
         }
-        if ((i % DW_DRAIN) == DW_DRAIN - 1 || i == my_units - 1) tc_commit(&acc_full[g]);
+        if ((i % DW_DRAIN) == DW_DRAIN - 1 || i == my_units - 1) {
+          if (elect_one_sync()) tc_commit(&acc_full[g]);
+          __syncwarp();
+        }
       }
     }
-    __syncwarp();
   } else if (warp >= 4 && warp < 12) {
     // =================== converter warpgroups (thread = channel = TMEM lane) ===================
     const int g = (warp - 4) >> 2;

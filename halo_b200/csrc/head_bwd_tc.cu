@@ -142,7 +142,7 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
 
   if (warp == 0) {
     // =================== TMA producer ===================
-    if (lane == 0) {
+    {
       const uint64_t pol = l2_policy_evict_last();
       int s = 0;
       uint32_t ph = 0;
@@ -152,21 +152,26 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
         const int p0 = (tile - n * a.tiles_per_img) * BT_BM;
         for (int j = 0; j < cpt; ++j) {
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], BT_STAGE_FLOATS * 4);
-          tma_load_2d_hint(ring + (size_t)s * BT_STAGE_FLOATS, &tmap, p0, n * C + j * BT_BK, &full[s], pol);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full[s], BT_STAGE_FLOATS * 4);
+            tma_load_2d_hint(ring + (size_t)s * BT_STAGE_FLOATS, &tmap, p0, n * C + j * BT_BK, &full[s], pol);
+          }
+          __syncwarp();
           if (++s == NST) { s = 0; ph ^= 1u; }
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
     // =================== MMA1 issuer: S, T (one main + one correction accumulator) ===================
-    if (lane == 0) {
+    // warp-wide loop, tcgen05 instructions on an elected lane (see elect_one_sync in tc_common.cuh)
+    {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t w_hi = __shfl_sync(0xffffffffu, smem_u32(sW), 0), w_lo = w_hi + (uint32_t)NR * C * 4;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
       const uint32_t lbo = NR * 16, sbo = 128;
       for (int i = 0; i < my_tiles; ++i) {
         const int b = i & 1;
-        const uint32_t d_main = tmem_base + BT_FG_COL + b * 2 * NP, d_corr = d_main + NP;
+        const uint32_t d_main = tb + BT_FG_COL + b * 2 * NP, d_corr = d_main + NP;
         mbar_wait(&g_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);   // MMA2 of tile i-2 has read the region
         tc_fence_after();
         for (int j = 0; j < cpt; ++j) {
@@ -175,52 +180,58 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
           for (int h = 0; h < 2; ++h) {
             mbar_wait(&a_full[h], (uint32_t)ca & 1u);
             tc_fence_after();
-            const uint32_t a_col = tmem_base + BT_A_COL + h * 2 * BT_HK;
+            const uint32_t a_col = tb + BT_A_COL + h * 2 * BT_HK;
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int ks = 0; ks < BT_HK / 8; ++ks) {
-              const uint32_t koff = (uint32_t)((j * BT_BK + h * BT_HK + ks * 8) / 4) * lbo;
-              const uint64_t b_hi = make_b_desc(w_hi + koff, lbo, sbo);
-              const uint64_t b_lo = make_b_desc(w_lo + koff, lbo, sbo);
-              const uint32_t first = (j == 0 && h == 0 && ks == 0) ? 0u : 1u;
-              tc_mma_tf32_ts(d_main, a_col + ks * 8, b_hi, idesc, first);
-              tc_mma_tf32_ts(d_corr, a_col + BT_HK + ks * 8, b_hi, idesc, first);
-              tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);
+              for (int ks = 0; ks < BT_HK / 8; ++ks) {
+                const uint32_t koff = (uint32_t)((j * BT_BK + h * BT_HK + ks * 8) / 4) * lbo;
+                const uint64_t b_hi = make_b_desc(w_hi + koff, lbo, sbo);
+                const uint64_t b_lo = make_b_desc(w_lo + koff, lbo, sbo);
+                const uint32_t first = (j == 0 && h == 0 && ks == 0) ? 0u : 1u;
+                tc_mma_tf32_ts(d_main, a_col + ks * 8, b_hi, idesc, first);
+                tc_mma_tf32_ts(d_corr, a_col + BT_HK + ks * 8, b_hi, idesc, first);
+                tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);
+              }
+              tc_commit(&a_empty[h]);
             }
-            tc_commit(&a_empty[h]);
+            __syncwarp();
           }
         }
-        tc_commit(&facc_full[b]);
+        if (elect_one_sync()) tc_commit(&facc_full[b]);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp == 3) {
     // =================== MMA2 issuer: D2[128 x C] = G . W ===================
-    if (lane == 0) {
+    {
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
       // D=f32, A=B=tf32, both K-major, N=C, M=128.  B rows = channels (16 B apart), K = n: chunks of 4 n are C*16 B apart
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(BT_BM >> 4) << 24);
       const uint32_t lbo = (uint32_t)C * 16, sbo = 128;
-      const uint32_t w2_hi = smem_u32(sW2), w2_lo = smem_u32(sW2 + (size_t)NR * C);
-      const uint32_t d2 = tmem_base + BT_D2_COL;
+      const uint32_t w2_hi = __shfl_sync(0xffffffffu, smem_u32(sW2), 0), w2_lo = w2_hi + (uint32_t)NR * C * 4;
+      const uint32_t d2 = tb + BT_D2_COL;
       for (int i = 0; i < my_tiles; ++i) {
         const int b = i & 1;
         mbar_wait(&g_full[b], (uint32_t)(i >> 1) & 1u);
         mbar_wait(d2_empty, ((uint32_t)i & 1u) ^ 1u);
         tc_fence_after();
-        const uint32_t g_col = tmem_base + BT_FG_COL + b * 2 * NP;
+        const uint32_t g_col = tb + BT_FG_COL + b * 2 * NP;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int ks = 0; ks < NR / 8; ++ks) {
-          const uint64_t b_hi = make_b_desc(w2_hi + 2 * ks * lbo, lbo, sbo);
-          const uint64_t b_lo = make_b_desc(w2_lo + 2 * ks * lbo, lbo, sbo);
-          const uint32_t g_hi = g_col + ks * 8, g_lo = g_hi + NP;
-          tc_mma_tf32_ts(d2, g_hi, b_hi, idesc, ks == 0 ? 0u : 1u);
-          tc_mma_tf32_ts(d2, g_lo, b_hi, idesc, 1u);
-          tc_mma_tf32_ts(d2, g_hi, b_lo, idesc, 1u);
+          for (int ks = 0; ks < NR / 8; ++ks) {
+            const uint64_t b_hi = make_b_desc(w2_hi + 2 * ks * lbo, lbo, sbo);
+            const uint64_t b_lo = make_b_desc(w2_lo + 2 * ks * lbo, lbo, sbo);
+            const uint32_t g_hi = g_col + ks * 8, g_lo = g_hi + NP;
+            tc_mma_tf32_ts(d2, g_hi, b_hi, idesc, ks == 0 ? 0u : 1u);
+            tc_mma_tf32_ts(d2, g_lo, b_hi, idesc, 1u);
+            tc_mma_tf32_ts(d2, g_hi, b_lo, idesc, 1u);
+          }
+          tc_commit(&g_empty[b]);
+          tc_commit(d2_full);
         }
-        tc_commit(&g_empty[b]);
-        tc_commit(d2_full);
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else if (warp >= 4 && warp < 8) {
     // =================== converters ===================
     const int wq = warp & 3, m = wq * 32 + lane;

@@ -160,8 +160,9 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     // =================== TMA producers: warp 0 feeds warpgroup 0, warp 2 feeds warpgroup 1 ===================
     // Each warpgroup owns a private ring (stages + barriers): a barrier then has exactly one producer and one
     // consumer advancing in lock-step, which the 1-bit mbarrier phase parity requires.
-    const int g = warp >> 1;
-    if (lane == 0) {
+    // (warp-wide loop, the TMA instruction on an elected lane: see elect_one_sync in tc_common.cuh)
+    const int g = __shfl_sync(0xffffffffu, warp >> 1, 0);
+    {
       for (int i = g; i < my_tiles; i += TC_NWG) {
         const int it = i / TC_NWG;
         const int tile = tc_tile_of(i, blockIdx.x, gridDim.x);
@@ -172,12 +173,14 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
           const int s = g * TC_WG_STAGES + q % TC_WG_STAGES;
           const uint32_t ph = (uint32_t)(q / TC_WG_STAGES) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], TC_STAGE_FLOATS * 4);
-          tma_load_2d(ring + (size_t)s * TC_STAGE_FLOATS, &tmap, p0, n * C + j * TC_BK, &full[s]);
+          if (elect_one_sync()) {
+            mbar_arrive_expect_tx(&full[s], TC_STAGE_FLOATS * 4);
+            tma_load_2d(ring + (size_t)s * TC_STAGE_FLOATS, &tmap, p0, n * C + j * TC_BK, &full[s]);
+          }
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else if (warp == 1 || warp == 3) {
     // =================== MMA issuers: warp 1 serves warpgroup 0, warp 3 serves warpgroup 1 ===================
     // One issuing thread per pixel warpgroup, each strictly in order for ITS warpgroup: the two conversion
