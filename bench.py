@@ -310,13 +310,13 @@ def run_ours(args):
         achieved = alg_bytes / (k_ms / 1e3) / 1e9
         traffic = None
         try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (scaled per image)
-            with open(os.path.join(ROOT, "profiles", "r1h_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r1n_traffic.json")) as f:
                 traffic = float(json.load(f)["dram_bytes_per_image"]) * B
         except Exception:
             traffic = None
         roof = {"bound": "hbm", "kernel": "head_fwd_tc_kernel (K1 fused head, tcgen05)", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-                "traffic_source": "profiles/r1h_traffic.json (ncu dram__bytes_read+write per launch)", "peak_source": peak_src,
+                "traffic_source": "profiles/r1n_traffic.json (ncu dram__bytes_read+write per launch)", "peak_source": peak_src,
                 "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
                 "step_frac": round((4.0 * C + 13) * px_step / world * args.steps / (ms_total / 1e3) / 1e9 / peak, 4)}
     if distributed:
