@@ -26,7 +26,7 @@ import torch  # noqa: E402
 WORKLOAD = dict(name="cfg2_gtav_cityscapes", pool_images=2975, H=640, W=1280, C=256, O=19, radius_k=1,
                 mask_radius_k=5, budget=0.05, n_rounds=1, uncertainty="entropy", purity="radius", normalize=True,
                 curvature=1.0, sigma=0.1)
-KERNELS_PER_STEP = 6  # head_pack, head_fwd, score_init, score_pass_a, score_pass_b, select
+KERNELS_PER_STEP = 7  # head_pack, head_pack_tc, head_fwd_tc, score_init, score_pass_a, score_pass_b, select
 
 
 def measured_peak_gbs():
@@ -248,10 +248,14 @@ def run_ours(args):
     def reset(s):
         s["active"].zero_(); s["selected"].zero_(); s["active_mask"].fill_(255)
 
+    # N > 1: every rank keeps a replica of the job's label masks; a step all-gathers the round's delta (pick counts, picks
+    # and the labels of their windows: 59 KB per image instead of the 819 KB plane) and replays it onto the replica
+    replica = torch.full((B * world, H, W), 255, dtype=torch.uint8, device=dev) if distributed else None
+
     def step(s):
-        res = halo_b200.acquire_batch(feat, P, A, cfg, gt, s["active"], s["selected"], s["active_mask"])
+        res = halo_b200.acquire_batch(feat, P, A, cfg, gt, s["active"], s["selected"], s["active_mask"], want_picks=distributed)
         if distributed:
-            pool.gather_round(res["n_picked"], s["active_mask"], B * world)
+            pool.gather_round_delta(res["n_picked"], res["picks"], gt, replica, B * world, cfg.radius_k)
         return res
 
     for i in range(args.warmup):
@@ -340,7 +344,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(B), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": KERNELS_PER_STEP * args.steps, "picks_per_image": picks_ok, "train_step": train,
+            "gpu_launches": (KERNELS_PER_STEP + (2 if distributed else 0)) * args.steps,  # + round_delta pack / apply
+            "picks_per_image": picks_ok, "train_step": train,
             "round_seconds_at_this_rate": round(w["pool_images"] * H * W / (value * 1e6), 4),
         }
         print(json.dumps(line), flush=True)

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "halo_select_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "halo_select_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "halo_select_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "halo_round_delta_pack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "halo_round_delta_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -161,6 +161,17 @@ int halo_select_f64(double* score, uint8_t* active, uint8_t* selected, uint8_t* 
                     int n_regions, int active_radius, int mask_radius, int flags, int* n_picked, int* picks,
                     int N, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
 
+/* ---- round deltas: compact exchange of a round's mask updates between image shards ------------
+ * A round labels the (2*active_radius+1)^2 windows around its picks (build.py:58-62).  pack gathers those labels:
+ *   picks [N,cap] i32 (as written by halo_select_*), n_picked [N] i32, gt [N,H,W] u8 ->
+ *   lab [N,cap,(2a+1)^2] u8 (gt of the window, row-major; 255 outside the image and for i >= n_picked).
+ * apply replays gathered deltas onto replicated masks: row j of the gathered buffers belongs to pool image
+ * row_image[j] (< 0: padding row, skipped);  masks [n_images,H,W] u8 receives masks[image][window] = lab. */
+int halo_round_delta_pack(const int* picks, const int* n_picked, const uint8_t* gt, uint8_t* lab, int N, int cap,
+                          int H, int W, int active_radius, halo_stream_t stream);
+int halo_round_delta_apply(uint8_t* masks, const int* row_image, const int* picks, const int* n_picked,
+                           const uint8_t* lab, int rows, int cap, int H, int W, int active_radius, halo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,3 +144,30 @@ def test_runs_on_a_side_stream_and_accepts_strided_inputs():
     side.synchronize()
     assert torch.equal(out["score"], ref["score"]) and torch.equal(out["n_picked"], ref["n_picked"])
 
+
+
+def test_round_delta_reproduces_the_masks_two_rounds():
+    """SURVEY 8e, compact exchange: picks + window labels of a round, replayed onto a replica, give the mask planes the
+    round wrote -- bit-exact, over two consecutive rounds (the second one starts from the first one's state)."""
+    from halo_b200 import pool
+
+    C, O, H, W, B = 32, 19, 96, 160, 3
+    cfg = halo_b200.AcquisitionConfig(num_classes=O, radius_k=1, budget=0.02, n_rounds=2)
+    P, A = synth.head_params(O, C, seed=1, device=DEV)
+    d = synth.batch(5, B, C, O, H, W, device=DEV)
+    replica = torch.full((B + 2, H, W), 255, dtype=torch.uint8, device=DEV)    # a pool of B+2 images, this shard owns 1..B
+    row_image = torch.arange(1, B + 1, dtype=torch.int32, device=DEV)
+    for rnd in range(2):
+        res = halo_b200.acquire_batch(d["feat"], P, A, cfg, d["gt"], d["active"], d["selected"], d["active_mask"],
+                                      want_picks=True)
+        lab = pool.pack_round_delta(res["picks"], res["n_picked"], d["gt"], cfg.radius_k)
+        # the CUDA kernels and the torch index arithmetic used for CPU tensors agree
+        lab_cpu = pool.pack_round_delta(res["picks"].cpu(), res["n_picked"].cpu(), d["gt"].cpu(), cfg.radius_k)
+        assert torch.equal(lab.cpu(), lab_cpu)
+        pool.apply_round_delta(replica, row_image, res["picks"], res["n_picked"], lab, cfg.radius_k)
+        assert torch.equal(replica[1:B + 1], d["active_mask"]), rnd
+        assert bool((replica[0] == 255).all()) and bool((replica[B + 1] == 255).all())
+        assert int(res["n_picked"].min()) > 0
+    out = pool.gather_round_delta(res["n_picked"], res["picks"], d["gt"], torch.full((B, H, W), 255, dtype=torch.uint8, device=DEV),
+                                  B, cfg.radius_k)
+    assert torch.equal(out["n_picked"], res["n_picked"])

@@ -106,3 +106,79 @@ def test_gather_round_world2_gloo(tmp_path, n_images):
         for i in range(n_images):
             assert int(o["active_mask"][i, 0, 0]) == i % 251
     assert torch.equal(outs[0]["active_mask"], outs[1]["active_mask"])
+
+
+def _delta_case(n_images, H, W, cap, r, seed=0):
+    """Synthetic picks per image (distinct centres, some on the border), gt, and the dense masks the round produces."""
+    g = torch.Generator().manual_seed(seed)
+    gt = torch.randint(0, 19, (n_images, H, W), generator=g, dtype=torch.int64).to(torch.uint8)
+    gt[torch.rand((n_images, H, W), generator=g) < 0.1] = 255
+    picks = torch.full((n_images, cap), -1, dtype=torch.int32)
+    cnt = torch.zeros((n_images,), dtype=torch.int32)
+    dense = torch.full((n_images, H, W), 255, dtype=torch.uint8)
+    for i in range(n_images):
+        n = int(torch.randint(0, cap + 1, (1,), generator=g))
+        centres = torch.randperm(H * W, generator=g)[:n]
+        centres[:2] = torch.tensor([0, H * W - 1])[:n]   # corner windows are clipped (build.py:45-48)
+        picks[i, :n] = centres.int()
+        cnt[i] = n
+        for p in centres.tolist():
+            h, w = divmod(p, W)
+            h0, h1, w0, w1 = max(h - r, 0), min(h + r + 1, H), max(w - r, 0), min(w + r + 1, W)
+            dense[i, h0:h1, w0:w1] = gt[i, h0:h1, w0:w1]
+    return gt, picks, cnt, dense
+
+
+def test_round_delta_pack_apply_cpu():
+    for r in (0, 1, 2):
+        gt, picks, cnt, dense = _delta_case(4, 9, 13, 7, r, seed=r)
+        lab = pool.pack_round_delta(picks, cnt, gt, r)
+        assert lab.shape == (4, 7, (2 * r + 1) ** 2) and lab.dtype == torch.uint8
+        masks = torch.full((4, 9, 13), 255, dtype=torch.uint8)
+        pool.apply_round_delta(masks, torch.arange(4, dtype=torch.int32), picks, cnt, lab, r)
+        assert torch.equal(masks, dense)
+        # padding rows and earlier labels are left alone
+        masks2 = torch.full((6, 9, 13), 7, dtype=torch.uint8)
+        pool.apply_round_delta(masks2, torch.tensor([5, -1, 0, -1], dtype=torch.int32), picks, cnt, lab, r)
+        assert torch.equal(masks2[1:5], torch.full((4, 9, 13), 7, dtype=torch.uint8))
+        out = pool.gather_round_delta(cnt, picks, gt, torch.full((4, 9, 13), 255, dtype=torch.uint8), 4, r)   # no process group
+        assert torch.equal(out["active_mask"], dense) and torch.equal(out["n_picked"], cnt)
+
+
+def _delta_worker(rank, world, port, n_images, tmp):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, W, cap, r = 8, 12, 6, 1
+        gt, picks, cnt, dense = _delta_case(n_images, H, W, cap, r, seed=3)
+        lo, hi = pool.shard_range(n_images, rank, world)
+        masks = torch.full((n_images, H, W), 255, dtype=torch.uint8)
+        masks[:, 0, 5] = 3   # a label from an earlier round (on a pixel no window of this case may change: see below)
+        out = pool.gather_round_delta(cnt[lo:hi] if hi > lo else None, picks[lo:hi] if hi > lo else None,
+                                      gt[lo:hi] if hi > lo else None, masks, n_images, r)
+        dense_all = pool.gather_round(cnt[lo:hi] if hi > lo else None, dense[lo:hi] if hi > lo else None, n_images)
+        torch.save({"delta": out, "dense": dense_all}, os.path.join(tmp, "d%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [5, 1])
+def test_gather_round_delta_world2_gloo(tmp_path, n_images):
+    """The compact exchange (picks + window labels) reproduces what the dense mask all-gather delivers."""
+    world = 2
+    mp.spawn(_delta_worker, args=(world, _free_port(), n_images, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(str(tmp_path), "d%d.pt" % r)) for r in range(world)]
+    for o in outs:
+        assert torch.equal(o["delta"]["n_picked"], o["dense"]["n_picked"])
+        got, ref = o["delta"]["active_mask"], o["dense"]["active_mask"]
+        touched = ref != 255
+        assert torch.equal(got[touched], ref[touched])
+        untouched = ~touched
+        untouched[:, 0, 5] = False
+        assert bool((got[untouched] == 255).all())
+        keep = ~touched[:, 0, 5]
+        assert bool((got[:, 0, 5][keep] == 3).all())   # the earlier round's label survives where this round wrote nothing
+    assert torch.equal(outs[0]["delta"]["active_mask"], outs[1]["delta"]["active_mask"])
