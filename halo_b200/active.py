@@ -101,7 +101,11 @@ def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_
     # PNG encoding + torch.save leave the loop: same files, written by a thread pool from pinned
     # staging buffers; flushed before this function returns, as the caller expects (train_learners.py:318-322 reloads
     # the dataset right after)
-    writer = AsyncMaskWriter(workers=int(getattr(cfg.ACTIVE, "IO_WORKERS", 4)))
+    try:
+        io_workers = int(cfg.ACTIVE.IO_WORKERS)   # optional key; the reference's config does not define it
+    except (AttributeError, KeyError):
+        io_workers = 4
+    writer = AsyncMaskWriter(workers=io_workers)
     with torch.no_grad(), writer:
         idx = 0
         for tgt_data in tgt_epoch_loader:

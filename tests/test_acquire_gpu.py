@@ -154,7 +154,7 @@ def test_round_delta_reproduces_the_masks_two_rounds():
     C, O, H, W, B = 32, 19, 96, 160, 3
     cfg = halo_b200.AcquisitionConfig(num_classes=O, radius_k=1, budget=0.02, n_rounds=2)
     P, A = synth.head_params(O, C, seed=1, device=DEV)
-    d = synth.batch(5, B, C, O, H, W, device=DEV)
+    d = synth.batch(5, 5 + B, C, O, H, W, device=DEV)
     replica = torch.full((B + 2, H, W), 255, dtype=torch.uint8, device=DEV)    # a pool of B+2 images, this shard owns 1..B
     row_image = torch.arange(1, B + 1, dtype=torch.int32, device=DEV)
     for rnd in range(2):
