@@ -226,6 +226,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     distributed = world > 1
     if distributed:
+        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     nat.load()
     cfg = make_cfg()
