@@ -29,6 +29,29 @@ WORKLOAD = dict(name="cfg2_gtav_cityscapes", pool_images=2975, H=640, W=1280, C=
 KERNELS_PER_STEP = 7  # head_pack, head_pack_tc, head_fwd_tc, score_init, score_pass_a, score_pass_b, select
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line.  Native libraries write there too (NCCL prints its version banner with
+    printf when NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the life of the
+    process and the JSON line goes to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -81,6 +104,20 @@ class ClockSampler(threading.Thread):
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers of the
+    end-to-end arm are first-touched on the GPU's own NUMA node (eight ranks otherwise share one node's memory
+    controllers and cross the socket interconnect on every H2D copy)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return True
+    except Exception:
+        return False
 
 
 def make_cfg():
@@ -188,7 +225,7 @@ def run_reference(args):
         "e2e": {"value": round(value, 5), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(batch, note=None):
@@ -224,10 +261,10 @@ def run_ours(args):
         raise RuntimeError("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    bind_to_gpu_numa_node(local)
     distributed = world > 1
     if distributed:
-        # stdout carries exactly one JSON line: NCCL's own banner / debug output (NCCL_DEBUG=VERSION|INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     nat.load()
     cfg = make_cfg()
@@ -339,6 +376,7 @@ def run_ours(args):
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
     e2e = run_e2e(args, cfg, P, A, dev, rank, world, distributed)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
+        os.sched_setaffinity(0, all_cpus)   # the CPU arm gets every host core again
         cpu = cpu_baseline()
     if rank == 0:
         line = {
@@ -350,7 +388,7 @@ def run_ours(args):
             "picks_per_image": picks_ok, "train_step": train,
             "round_seconds_at_this_rate": round(w["pool_images"] * H * W / (value * 1e6), 4),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if distributed:
         dist.destroy_process_group()
 
@@ -469,6 +507,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the configs[4] fwd+bwd side measurement")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
