@@ -117,17 +117,21 @@ __device__ __forceinline__ PixelScalars ball_scalars(double n2, const HeadConsts
 }
 
 // asinh through the SFU, branch-free: sign(x) * ln(|x| + sqrt(x^2+1)); absolute error ~2e-7, which the logit
-// tolerance (1e-5 of max|logit|) absorbs with a wide margin (DESIGN.md "K1 numerics").
+// tolerance (1e-5 of max|logit|) absorbs with a wide margin (DESIGN.md "K1 numerics").  One lg2: beyond 1e9 (x^2
+// overflows past ~1.8e19) the ARGUMENT of the logarithm is switched to 2|x| instead of computing two logarithms.
 __device__ __forceinline__ float fast_asinh(float x) {
   const float ax = fabsf(x);
   const float v = fmaf(ax, ax, 1.f);
-  const float r_mid = fast_ln(ax + v * fast_rsqrt(v));
-  const float r_big = fast_ln(ax) + 0.69314718f;  // x^2 overflows beyond ~1.8e19
-  return copysignf(ax > 1e9f ? r_big : r_mid, x);
+  const float t = (ax > 1e9f) ? 2.f * ax : ax + v * fast_rsqrt(v);
+  return copysignf(fast_ln(t), x);
 }
 
-// HyperMLR logit for one class from the two contractions (hyperbolic.py:146-183).  Both branches of the
-// MLR-ball projection are evaluated and selected (no divergence inside the warp).
+// HyperMLR logit for one class from the two contractions (hyperbolic.py:146-183).  Both sides of the MLR-ball
+// projection share ONE reciprocal square root: with D > 0, omc = bo/D and m = (1 - omc)/c,
+//   inside  (omc >= om_max  <=>  bo >= om_max*D):  arg = 2s * num / den,                den = max(bo, 1e-12 D)   (:179-180)
+//   outside (projected to maxnorm, :162-170):      arg = out_scale * num / (D sqrt(m)),  (D sqrt(m))^2 = D (D - bo) / c
+// so arg = k * num * rsqrt(X2) with (k, X2) selected per side -- 3 MUFU per class (this rsqrt, asinh's rsqrt and lg2)
+// instead of 6; the epilogue warpgroup was the busiest role of K1 (profiles/r1_k1.md r1o).
 __device__ __forceinline__ float mlr_logit(float S, float T, const PixelScalars& ps, float pp, float an, float pa,
                                            float Bk, const HeadConsts& hc) {
   const float px = ps.gamma * S;
@@ -136,15 +140,13 @@ __device__ __forceinline__ float mlr_logit(float S, float T, const PixelScalars&
   const float Anum = 1.f + cpx2 + ps.t2;                                  // :150
   const float D = fmaxf(fmaf(hc.c * ps.t2, pp, 1.f + cpx2), 1e-12f);      // :152-153
   const float num = fmaf(Bk, xa, Anum * pa);                              // D * <(-p)(+)x, a_hat>   (:175-177)
-  const float bo = Bk * ps.omega;
-  const float invD = fast_rcp(D);
-  const float omc = bo * invD;                                            // 1 - c*|(-p)(+)x|^2
-  // inside the MLR ball: D cancels (:179-180)
-  const float arg_in = hc.two_s * num * fast_rcp(fmaxf(bo, 1e-12f * D));
-  // outside: projected to maxnorm (:162-170)
-  const float m = fmaxf(1.f - omc, 0.f) * hc.inv_c;                       // |(-p)(+)x|^2
-  const float arg_out = num * invD * hc.out_scale * fast_rsqrt(fmaxf(m, 1e-24f));
-  const float arg = (omc >= hc.om_max) ? arg_in : arg_out;
+  const float bo = Bk * ps.omega;                                         // D * (1 - c*|(-p)(+)x|^2)
+  const bool inside = bo >= hc.om_max * D;
+  const float den = fmaxf(bo, 1e-12f * D);
+  const float x2_out = fmaxf(D * fmaxf(D - bo, 0.f) * hc.inv_c, D * D * 1e-24f);   // m clamped at 1e-24 as before
+  const float x2 = inside ? den * den : x2_out;
+  const float k = inside ? hc.two_s : hc.out_scale;
+  const float arg = num * k * fast_rsqrt(fmaxf(x2, 1e-36f));
   return hc.two_over_s * an * fast_asinh(arg);                            // :181-183 (lambda_term = 2.0)
 }
 
