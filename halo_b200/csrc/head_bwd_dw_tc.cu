@@ -28,7 +28,10 @@
 namespace halo {
 
 constexpr int DW_CHUNK = 32;                 // pixels per pipeline stage (128-byte rows)
-constexpr int DW_UNIT_CHUNKS = 4;            // consecutive chunks per work unit (512 contiguous bytes of every row)
+#ifndef HALO_DW_UNIT_CHUNKS
+#define HALO_DW_UNIT_CHUNKS 4
+#endif
+constexpr int DW_UNIT_CHUNKS = HALO_DW_UNIT_CHUNKS;   // consecutive chunks per work unit (4: 512 contiguous bytes of every row)
 constexpr int DW_DRAIN = 16;                 // units per accumulator chain
 constexpr int DW_TC_THREADS = 512;
 constexpr int DW_U_BOX_BYTES = 128 * DW_CHUNK * 4;   // 16 KB: one channel block of one chunk
