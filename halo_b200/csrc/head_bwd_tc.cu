@@ -36,6 +36,21 @@ constexpr int BT_TMEM_COLS = 512;
 // TMEM columns: A halves [0,64) | S,T -> G region of even tiles [64, 64+2NP) | of odd tiles [.., +2NP) | D2 [256, 256+C)
 constexpr int BT_A_COL = 0, BT_FG_COL = 64, BT_D2_COL = 256;
 
+// i-th tile of CTA b (G CTAs): every CTA takes RUNS of BT_RUN consecutive 128-pixel tiles (b*R .. b*R+R-1, then +R*G ...),
+// so it touches R*512 contiguous bytes of every channel row within a short window (DRAM page locality of the feature
+// reads, the re-reads and the du stores), like K1's adjacent-tile mapping.
+#ifndef HALO_BT_RUN
+#define HALO_BT_RUN 2
+#endif
+constexpr int BT_RUN = HALO_BT_RUN;
+__device__ __forceinline__ int bt_tile_of(int i, int b, int G) { return (i / BT_RUN) * (BT_RUN * G) + b * BT_RUN + (i % BT_RUN); }
+__device__ __forceinline__ int bt_my_tiles(int total, int b, int G) {
+  const int per_round = BT_RUN * G;
+  const int rounds = total / per_round, rem = total - rounds * per_round;
+  const int tail = rem - b * BT_RUN;
+  return rounds * BT_RUN + (tail <= 0 ? 0 : (tail >= BT_RUN ? BT_RUN : tail));
+}
+
 struct BwdTcArgs {
   const float* feat;
   const float* dlogits;
@@ -69,6 +84,53 @@ __host__ __device__ inline BtSmem bt_smem_layout(int NP, int OP, int C) {
   L.red_off = L.alpha_off + 2 * BT_BM * 4;
   L.total = L.red_off + (size_t)4 * 3 * OP * 4;
   return L;
+}
+
+// du[c][p] = alpha * u[c][p] + D2[p][c] for the channels [c_lo, c_hi) (multiples of 32) of this thread's pixel.
+// The features do not depend on D2: the first two channel groups (2 x 32 loads per thread) are requested before waiting
+// for the MMA, and two groups stay in flight under the TMEM read / store of the current one.  The re-read misses L2 two
+// times out of three (profiles/r1_k4.md), so this stage lives on memory-level parallelism -- which is why BOTH the
+// derivative warpgroup (after it has handed G to MMA2) and the output warpgroup run it, on disjoint channel ranges.
+__device__ __forceinline__ void bt_output_range(const float* ubase, float* dbase, size_t HW, bool live, uint32_t d2_taddr,
+                                                int c_lo, int c_hi, uint64_t* d2_full, uint32_t parity, const float* alpha_ptr) {
+  // rebase on the first channel of the range: the loop below then indexes from a literal 0, which is what lets ptxas
+  // fold every address into base + immediate * stride (with a run-time start it kept 60 channel indices on the stack)
+  ubase += (size_t)c_lo * HW;
+  dbase += (size_t)c_lo * HW;
+  d2_taddr += (uint32_t)c_lo;
+  const int Cn = c_hi - c_lo;
+  float ua[32], ub[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) ua[e] = (live && Cn > 0) ? __ldcs(ubase + (size_t)e * HW) : 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) ub[e] = (live && Cn > 32) ? __ldcs(ubase + (size_t)(32 + e) * HW) : 0.f;
+  mbar_wait(d2_full, parity);
+  tc_fence_after();
+  const float alpha = *alpha_ptr;
+  for (int c0 = 0; c0 < Cn; c0 += 64) {
+    float d[32];
+    tmem_ld_x32(d2_taddr + c0, d);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      if (live) __stcs(dbase + (size_t)(c0 + e) * HW, fmaf(alpha, ua[e], d[e]));
+    }
+    if (c0 + 64 < Cn) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) ua[e] = live ? __ldcs(ubase + (size_t)(c0 + 64 + e) * HW) : 0.f;
+    }
+    if (c0 + 32 >= Cn) break;   // an odd number of 32-channel groups
+    tmem_ld_x32(d2_taddr + c0 + 32, d);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      if (live) __stcs(dbase + (size_t)(c0 + 32 + e) * HW, fmaf(alpha, ub[e], d[e]));
+    }
+    if (c0 + 96 < Cn) {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) ub[e] = live ? __ldcs(ubase + (size_t)(c0 + 96 + e) * HW) : 0.f;
+    }
+  }
 }
 
 template <int NP, int OP>
@@ -121,7 +183,7 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
       mbar_init(&facc_full[i], 1); mbar_init(&g_full[i], 4); mbar_init(&g_empty[i], 1);
       mbar_init(&alpha_free[i], 4);
     }
-    mbar_init(d2_full, 1);   mbar_init(d2_empty, 4);
+    mbar_init(d2_full, 1);   mbar_init(d2_empty, 8);   // derivative + output warps
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -137,7 +199,14 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
 
   const int HW = a.HW;
   const int cpt = C / BT_BK;
-  const int my_tiles = (blockIdx.x < a.total_tiles) ? (a.total_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // output pass: derivative warpgroup [0, c_split), output warpgroup [c_split, C).  A quarter, not half: the derivative
+  // math itself takes about as long as the output pass of half a tile (r1p: with an even split the derivative warpgroup
+  // never waited and the output warpgroup idled 29 % of the time)
+#ifndef HALO_BT_SPLIT_DIV
+#define HALO_BT_SPLIT_DIV 128
+#endif
+  const int c_split = (C / HALO_BT_SPLIT_DIV) * 32;
+  const int my_tiles = bt_my_tiles(a.total_tiles, blockIdx.x, gridDim.x);
   const uint32_t w_hi = smem_u32(sW), w_lo = smem_u32(sW + (size_t)NR * C);
 
   if (warp == 0) {
@@ -147,7 +216,7 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const int tile = blockIdx.x + i * gridDim.x;
+        const int tile = bt_tile_of(i, blockIdx.x, gridDim.x);
         const int n = tile / a.tiles_per_img;
         const int p0 = (tile - n * a.tiles_per_img) * BT_BM;
         for (int j = 0; j < cpt; ++j) {
@@ -269,11 +338,11 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
     // =================== derivative warps (thread = pixel) ===================
     const int wq = warp & 3, m = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    const HeadConsts hc = a.hc;
+    const HeadConsts& hc = a.hc;   // operands straight from the constant bank: a register copy pushed this role past 128 registers
     const int O = a.O;
     for (int i = 0; i < my_tiles; ++i) {
       const int b = i & 1;
-      const int tile = blockIdx.x + i * gridDim.x;
+      const int tile = bt_tile_of(i, blockIdx.x, gridDim.x);
       const int n = tile / a.tiles_per_img;
       const int p = (tile - n * a.tiles_per_img) * BT_BM + m;
       const bool live = (p < HW);
@@ -353,55 +422,29 @@ head_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const BwdTcArgs a, 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&g_full[b]);
+      // second job of this warpgroup: the output pass of the lower channels of the same tile (see bt_output_range)
+      bt_output_range(a.feat + (size_t)n * C * HW + p, a.dfeat + (size_t)n * C * HW + p, (size_t)HW, live,
+                      tmem_base + lane_addr + BT_D2_COL, 0, c_split, d2_full, (uint32_t)i & 1u, &sAlpha[b * BT_BM + m]);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(d2_empty);
     }
   } else if (warp >= 12) {
     // =================== output warps (thread = pixel): du = D2 + alpha * u ===================
     const int wq = warp & 3, m = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
     for (int i = 0; i < my_tiles; ++i) {
-      const int tile = blockIdx.x + i * gridDim.x;
+      const int tile = bt_tile_of(i, blockIdx.x, gridDim.x);
       const int n = tile / a.tiles_per_img;
       const int p = (tile - n * a.tiles_per_img) * BT_BM + m;
       const bool live = (p < HW);
       const float* ubase = a.feat + (size_t)n * C * HW + p;
       float* dbase = a.dfeat + (size_t)n * C * HW + p;
-      // The features do not depend on D2: the first two channel groups (2 x 32 loads per thread) are requested before
-      // waiting for the MMA, and two groups stay in flight under the TMEM read / store of the current one.  The re-read
-      // misses L2 two times out of three (profiles/r1_k4.md), so this stage lives on memory-level parallelism.
-      float ua[32], ub[32];
-#pragma unroll
-      for (int e = 0; e < 32; ++e) ua[e] = live ? __ldcs(ubase + (size_t)e * HW) : 0.f;
-#pragma unroll
-      for (int e = 0; e < 32; ++e) ub[e] = live ? __ldcs(ubase + (size_t)(32 + e) * HW) : 0.f;
-      mbar_wait(d2_full, (uint32_t)i & 1u);
-      tc_fence_after();
-      const float alpha = sAlpha[(i & 1) * BT_BM + m];
+      // channels [c_split, C); the derivative warpgroup takes [0, c_split) of the same tile
+      bt_output_range(ubase, dbase, (size_t)HW, live, tmem_base + lane_addr + BT_D2_COL, c_split, C, d2_full, (uint32_t)i & 1u,
+                      &sAlpha[(i & 1) * BT_BM + m]);
       __syncwarp();
       if (lane == 0) mbar_arrive(&alpha_free[i & 1]);
-      for (int c0 = 0; c0 < C; c0 += 64) {
-        float d[32];
-        tmem_ld_x32(tmem_base + lane_addr + BT_D2_COL + c0, d);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          if (live) __stcs(dbase + (size_t)(c0 + e) * HW, fmaf(alpha, ua[e], d[e]));
-        }
-        if (c0 + 64 < C) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) ua[e] = live ? __ldcs(ubase + (size_t)(c0 + 64 + e) * HW) : 0.f;
-        }
-        if (c0 + 32 >= C) break;   // C = 96, 160, 224: an odd number of channel groups
-        tmem_ld_x32(tmem_base + lane_addr + BT_D2_COL + c0 + 32, d);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          if (live) __stcs(dbase + (size_t)(c0 + 32 + e) * HW, fmaf(alpha, ub[e], d[e]));
-        }
-        if (c0 + 96 < C) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) ub[e] = live ? __ldcs(ubase + (size_t)(c0 + 96 + e) * HW) : 0.f;
-        }
-      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(d2_empty);
@@ -448,8 +491,9 @@ bool head_bwd_tc_supported(int C, int O, int H, int W, const void* feat, const v
 
 int head_bwd_tc_grid(int N, int HW) {
   const int tiles = ((HW + BT_BM - 1) / BT_BM) * N;
+  const int runs = (tiles + BT_RUN - 1) / BT_RUN;
   int g = sm_count();
-  return g < tiles ? g : tiles;
+  return g < runs ? g : runs;
 }
 
 template <int NP, int OP>
