@@ -220,9 +220,11 @@ __device__ __forceinline__ PixelScalarGrads tangent_scalar_grads(float n2, const
 
 // One class: upstream gradient G of the logit -> gradients w.r.t. the two contractions (gS, gT), accumulated
 // gradients w.r.t. the per-pixel scalars (g_gamma, g_t2, g_om) and the class scalars (d_pp, d_an, d_pa).
-// Branch-free (both sides of the MLR-ball projection are evaluated and selected) and on single-MUFU
-// approximations like the forward epilogue: ~60 instructions per class instead of ~330 with IEEE division,
-// libm asinhf and a divergent branch (profiles/r1_k4.md).
+// Same single-rsqrt form as mlr_logit: arg = k * num * rsqrt(X2) with
+//   inside  (bo >= om_max*D):  k = 2s,        X2 = den^2, den = max(bo, 1e-12 D)   d arg/d bo = -arg/den,  d arg/d D = 0
+//   outside (projected):       k = out_scale, X2 = D (D - bo) / c                  d arg/d X2 = -arg / (2 X2),
+//                                                                                  d X2/d D = (2D - bo)/c,  d X2/d bo = -D/c
+// Branch-free, 3 MUFU per class (this rsqrt, rsqrt(1 + arg^2) shared with asinh, lg2).
 __device__ __forceinline__ void mlr_logit_grad(float G, float S, float T, const PixelScalarGrads& ps, float pp, float an,
                                                float pa, float Bk, const HeadConsts& hc, float& gS, float& gT,
                                                float& g_gamma, float& g_t2, float& g_om, float& d_pp, float& d_an,
@@ -235,29 +237,25 @@ __device__ __forceinline__ void mlr_logit_grad(float G, float S, float T, const 
   const float D = fmaxf(Draw, 1e-12f);
   const float num = fmaf(Bk, xa, Anum * pa);
   const float bo = Bk * ps.omega;
-  const float invD = fast_rcp(D);
-  const float omc = bo * invD;
-  const bool inside = omc >= hc.om_max;
-  // inside the MLR ball: arg = 2s * num / bo
-  const float inv_den = fast_rcp(fmaxf(bo, 1e-12f * D));
-  const float a_num_in = hc.two_s * inv_den;
-  const float arg_in = num * a_num_in;
-  const float a_bo_in = -arg_in * inv_den;
-  // projected to maxnorm: arg = num / D * out_scale / sqrt(m),  m = (1 - omc) / c
-  const float m = fmaxf(1.f - omc, 0.f) * hc.inv_c;
-  const float rinv = fast_rsqrt(fmaxf(m, 1e-24f));   // 1 / max(sqrt(m), 1e-12)
-  const float a_num_out = invD * hc.out_scale * rinv;
-  const float arg_out = num * a_num_out;
-  const float a_m = -0.5f * arg_out * rinv * rinv;   // d arg / d m
-  const float a_bo_out = -a_m * invD * hc.inv_c;
-  const float a_D_out = invD * fmaf(a_m * omc, hc.inv_c, -arg_out);
-  const float arg = inside ? arg_in : arg_out;
-  const float a_num = inside ? a_num_in : a_num_out;
-  const float a_bo = inside ? a_bo_in : a_bo_out;
-  const float a_D = (inside || dclamp) ? 0.f : a_D_out;
-  const float ash = fast_asinh(arg);
+  const bool inside = bo >= hc.om_max * D;
+  const float den = fmaxf(bo, 1e-12f * D);
+  const float dmb = D - bo;                                   // D * c * m
+  const bool mclamp = dmb <= D * 1e-24f * hc.c;               // m clamped at 1e-24: no gradient through it
+  const float x2_out = fmaxf(D * fmaxf(dmb, 0.f) * hc.inv_c, D * D * 1e-24f);
+  const float x2 = inside ? den * den : x2_out;
+  const float rinv = fast_rsqrt(fmaxf(x2, 1e-36f));
+  const float a_num = (inside ? hc.two_s : hc.out_scale) * rinv;
+  const float arg = num * a_num;
+  const float q = arg * rinv * rinv * (0.5f * hc.inv_c);      // arg / (2 c X2)
+  const float a_bo = inside ? -arg * rinv : (mclamp ? 0.f : q * D);
+  const float a_D = (inside || dclamp || mclamp) ? 0.f : -q * (2.f * D - bo);
+  // asinh(arg) and its derivative 1/sqrt(1 + arg^2) share the rsqrt
+  const float ax = fabsf(arg);
+  const float v = fmaf(ax, ax, 1.f);
+  const float rs = fast_rsqrt(v);
+  const float ash = copysignf(fast_ln((ax > 1e9f) ? 2.f * ax : ax + v * rs), arg);
   const float gl = G * hc.two_over_s;
-  const float g = gl * an * fast_rsqrt(fmaf(arg, arg, 1.f));
+  const float g = gl * an * rs;
   const float g_num = g * a_num, g_bo = g * a_bo, g_D = g * a_D;
   const float g_Bk = fmaf(g_num, xa, g_bo * ps.omega);
   const float g_xa = g_num * Bk;
