@@ -162,60 +162,42 @@ def gather_round(n_picked_local, mask_local, n_images, *, group=None, device=Non
 # ---- compact exchange: round deltas instead of mask planes -----------------------------------------------------
 def pack_round_delta(picks, n_picked, gt, active_radius):
     """Labels a round wrote around its picks: lab (N,cap,(2a+1)^2) uint8, 255 outside the image / beyond n_picked
-    (build.py:58-62: active_mask[window] = ground_truth[window]).  CUDA tensors go through halo_round_delta_pack;
-    CPU tensors (the gloo plumbing tests) through the same index arithmetic in torch."""
+    (build.py:58-62: active_mask[window] = ground_truth[window]) -- halo_round_delta_pack.  CUDA tensors only."""
+    nat.require_cuda(picks, "picks")
     N, cap = picks.shape
     H, W = gt.shape[-2:]
     r = int(active_radius)
     k = 2 * r + 1
-    if picks.is_cuda:
-        lib = nat.load()
-        lab = torch.empty((N, cap, k * k), dtype=torch.uint8, device=picks.device)
-        with torch.cuda.device(picks.device):
-            rc = lib.halo_round_delta_pack(nat.ptr(picks), nat.ptr(n_picked), nat.ptr(gt), nat.ptr(lab), N, cap, H, W, r,
-                                           nat.stream_of(picks))
-        nat.check(rc, "halo_round_delta_pack")
-        return lab
-    valid = (picks >= 0) & (torch.arange(cap)[None, :] < n_picked[:, None])
-    p = picks.clamp_min(0).long()
-    d = torch.arange(-r, r + 1)
-    hh = (p // W)[..., None, None] + d[:, None]
-    ww = (p % W)[..., None, None] + d[None, :]
-    inside = ((hh >= 0) & (hh < H) & (ww >= 0) & (ww < W) & valid[..., None, None]).reshape(N, cap * k * k)
-    flat = (hh.clamp(0, H - 1) * W + ww.clamp(0, W - 1)).reshape(N, cap * k * k)
-    lab = torch.gather(gt.reshape(N, H * W), 1, flat)
-    return torch.where(inside, lab, torch.full_like(lab, 255)).reshape(N, cap, k * k)
+    lib = nat.load()
+    lab = torch.empty((N, cap, k * k), dtype=torch.uint8, device=picks.device)
+    with torch.cuda.device(picks.device):
+        rc = lib.halo_round_delta_pack(nat.ptr(picks), nat.ptr(n_picked), nat.ptr(gt), nat.ptr(lab), N, cap, H, W, r,
+                                       nat.stream_of(picks))
+    nat.check(rc, "halo_round_delta_pack")
+    return lab
 
 
 def apply_round_delta(masks, row_image, picks, n_picked, lab, active_radius):
     """masks (n_images,H,W) uint8 replica, updated IN PLACE: row j of (picks, n_picked, lab) belongs to pool image
-    row_image[j] (negative = padding row)."""
+    row_image[j] (negative = padding row) -- halo_round_delta_apply.  CUDA tensors only."""
+    nat.require_cuda(masks, "masks")
     rows, cap = picks.shape
     H, W = masks.shape[-2:]
-    r = int(active_radius)
-    k = 2 * r + 1
-    if masks.is_cuda:
-        lib = nat.load()
-        with torch.cuda.device(masks.device):
-            rc = lib.halo_round_delta_apply(nat.ptr(masks), nat.ptr(row_image), nat.ptr(picks), nat.ptr(n_picked), nat.ptr(lab),
-                                            rows, cap, H, W, r, nat.stream_of(masks))
-        nat.check(rc, "halo_round_delta_apply")
-        return masks
-    valid = (picks >= 0) & (torch.arange(cap)[None, :] < n_picked[:, None]) & (row_image[:, None] >= 0)
-    p = picks.clamp_min(0).long()
-    d = torch.arange(-r, r + 1)
-    hh = (p // W)[..., None, None] + d[:, None]
-    ww = (p % W)[..., None, None] + d[None, :]
-    inside = (hh >= 0) & (hh < H) & (ww >= 0) & (ww < W) & valid[..., None, None] & (lab.reshape(rows, cap, k, k) != 255)
-    flat = row_image.clamp_min(0).long()[:, None, None, None] * (H * W) + hh * W + ww
-    masks.view(-1)[flat[inside]] = lab.reshape(rows, cap, k, k)[inside]
+    lib = nat.load()
+    with torch.cuda.device(masks.device):
+        rc = lib.halo_round_delta_apply(nat.ptr(masks), nat.ptr(row_image), nat.ptr(picks), nat.ptr(n_picked), nat.ptr(lab),
+                                        rows, cap, H, W, int(active_radius), nat.stream_of(masks))
+    nat.check(rc, "halo_round_delta_apply")
     return masks
 
 
-def gather_round_delta(n_picked_local, picks_local, gt_local, masks, n_images, active_radius, *, group=None):
+def gather_round_delta(n_picked_local, picks_local, gt_local, masks, n_images, active_radius, *, group=None,
+                       pack=pack_round_delta, apply=apply_round_delta):
     """Compact form of `gather_round`: all-gather (pick counts, picks, window labels) -- 13 B per pick for 3x3 regions
     instead of H*W bytes per image -- and replay them onto `masks` (n_images,H,W) uint8, this rank's replica of the
     pool's label masks (the labels of earlier rounds stay).  Works without a process group (single shard) too.
+    `pack` / `apply` are the two CUDA entry points above; the world_size-2 gloo test, which has no GPU, passes the
+    oracle's restatement of them (oracle/delta.py) to exercise the sharding and the collective on CPU tensors.
     Returns {"n_picked": (n_images,) int32, "active_mask": masks}."""
     import torch.distributed as dist
 
@@ -238,7 +220,7 @@ def gather_round_delta(n_picked_local, picks_local, gt_local, masks, n_images, a
     if n_local:
         cnt_pad[:n_local] = n_picked_local
         pk_pad[:n_local] = picks_local
-        lab_pad[:n_local] = pack_round_delta(picks_local, n_picked_local, gt_local, active_radius)
+        lab_pad[:n_local] = pack(picks_local, n_picked_local, gt_local, active_radius)
     if distributed:
         cnt_all = torch.empty((world * per,), dtype=torch.int32, device=dev)
         pk_all = torch.empty((world * per, cap), dtype=torch.int32, device=dev)
@@ -249,7 +231,7 @@ def gather_round_delta(n_picked_local, picks_local, gt_local, masks, n_images, a
     else:
         cnt_all, pk_all, lab_all = cnt_pad, pk_pad, lab_pad
     row_image, keep_t = _row_maps(n_images, world, dev)
-    apply_round_delta(masks, row_image, pk_all, cnt_all, lab_all, active_radius)
+    apply(masks, row_image, pk_all, cnt_all, lab_all, active_radius)
     return {"n_picked": cnt_all.index_select(0, keep_t), "active_mask": masks}
 
 

@@ -150,6 +150,7 @@ def test_round_delta_reproduces_the_masks_two_rounds():
     """SURVEY 8e, compact exchange: picks + window labels of a round, replayed onto a replica, give the mask planes the
     round wrote -- bit-exact, over two consecutive rounds (the second one starts from the first one's state)."""
     from halo_b200 import pool
+    from oracle import delta as odelta
 
     C, O, H, W, B = 32, 19, 96, 160, 3
     cfg = halo_b200.AcquisitionConfig(num_classes=O, radius_k=1, budget=0.02, n_rounds=2)
@@ -161,11 +162,14 @@ def test_round_delta_reproduces_the_masks_two_rounds():
         res = halo_b200.acquire_batch(d["feat"], P, A, cfg, d["gt"], d["active"], d["selected"], d["active_mask"],
                                       want_picks=True)
         lab = pool.pack_round_delta(res["picks"], res["n_picked"], d["gt"], cfg.radius_k)
-        # the CUDA kernels and the torch index arithmetic used for CPU tensors agree
-        lab_cpu = pool.pack_round_delta(res["picks"].cpu(), res["n_picked"].cpu(), d["gt"].cpu(), cfg.radius_k)
+        # the CUDA kernels agree with the oracle's restatement (oracle/delta.py)
+        lab_cpu = odelta.pack_round_delta(res["picks"].cpu(), res["n_picked"].cpu(), d["gt"].cpu(), cfg.radius_k)
         assert torch.equal(lab.cpu(), lab_cpu)
+        ref = odelta.apply_round_delta(replica.cpu(), row_image.cpu(), res["picks"].cpu(), res["n_picked"].cpu(), lab_cpu,
+                                       cfg.radius_k)
         pool.apply_round_delta(replica, row_image, res["picks"], res["n_picked"], lab, cfg.radius_k)
         assert torch.equal(replica[1:B + 1], d["active_mask"]), rnd
+        assert torch.equal(replica.cpu(), ref), rnd
         assert bool((replica[0] == 255).all()) and bool((replica[B + 1] == 255).all())
         assert int(res["n_picked"].min()) > 0
     out = pool.gather_round_delta(res["n_picked"], res["picks"], d["gt"], torch.full((B, H, W), 255, dtype=torch.uint8, device=DEV),

@@ -11,6 +11,7 @@ import torch.multiprocessing as mp
 import halo_b200
 from halo_b200 import pool
 from oracle import acquire as oacquire
+from oracle import delta as odelta
 
 
 def test_shard_range_partitions_the_pool():
@@ -129,19 +130,22 @@ def _delta_case(n_images, H, W, cap, r, seed=0):
     return gt, picks, cnt, dense
 
 
-def test_round_delta_pack_apply_cpu():
+def test_round_delta_oracle_and_gather_plumbing_cpu():
     for r in (0, 1, 2):
         gt, picks, cnt, dense = _delta_case(4, 9, 13, 7, r, seed=r)
-        lab = pool.pack_round_delta(picks, cnt, gt, r)
+        lab = odelta.pack_round_delta(picks, cnt, gt, r)
         assert lab.shape == (4, 7, (2 * r + 1) ** 2) and lab.dtype == torch.uint8
         masks = torch.full((4, 9, 13), 255, dtype=torch.uint8)
-        pool.apply_round_delta(masks, torch.arange(4, dtype=torch.int32), picks, cnt, lab, r)
+        odelta.apply_round_delta(masks, torch.arange(4, dtype=torch.int32), picks, cnt, lab, r)
         assert torch.equal(masks, dense)
         # padding rows and earlier labels are left alone
         masks2 = torch.full((6, 9, 13), 7, dtype=torch.uint8)
-        pool.apply_round_delta(masks2, torch.tensor([5, -1, 0, -1], dtype=torch.int32), picks, cnt, lab, r)
+        odelta.apply_round_delta(masks2, torch.tensor([5, -1, 0, -1], dtype=torch.int32), picks, cnt, lab, r)
         assert torch.equal(masks2[1:5], torch.full((4, 9, 13), 7, dtype=torch.uint8))
-        out = pool.gather_round_delta(cnt, picks, gt, torch.full((4, 9, 13), 255, dtype=torch.uint8), 4, r)   # no process group
+        out = pool.gather_round_delta(cnt, picks, gt, torch.full((4, 9, 13), 255, dtype=torch.uint8), 4, r,
+                                      pack=odelta.pack_round_delta, apply=odelta.apply_round_delta)   # no process group
+        with pytest.raises(RuntimeError, match="no CPU path"):   # the product's own pack / apply are CUDA entry points
+            pool.pack_round_delta(picks, cnt, gt, r)
         assert torch.equal(out["active_mask"], dense) and torch.equal(out["n_picked"], cnt)
 
 
@@ -158,7 +162,8 @@ def _delta_worker(rank, world, port, n_images, tmp):
         masks = torch.full((n_images, H, W), 255, dtype=torch.uint8)
         masks[:, 0, 5] = 3   # a label from an earlier round (on a pixel no window of this case may change: see below)
         out = pool.gather_round_delta(cnt[lo:hi] if hi > lo else None, picks[lo:hi] if hi > lo else None,
-                                      gt[lo:hi] if hi > lo else None, masks, n_images, r)
+                                      gt[lo:hi] if hi > lo else None, masks, n_images, r,
+                                      pack=odelta.pack_round_delta, apply=odelta.apply_round_delta)
         dense_all = pool.gather_round(cnt[lo:hi] if hi > lo else None, dense[lo:hi] if hi > lo else None, n_images)
         torch.save({"delta": out, "dense": dense_all}, os.path.join(tmp, "d%d.pt" % rank))
     finally:
