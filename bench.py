@@ -365,6 +365,11 @@ def run_ours(args):
     if distributed:
         dist.barrier()
 
+    # ---- the other acquisition configurations of BASELINE.json / SURVEY 8(d), short runs on the same resident batch ----
+    others = None
+    if rank == 0 and world == 1 and not args.no_side_configs:
+        others = run_side_configs(feat, gt, state[0], dev)
+
     # ---- BASELINE.json configs[4] beside it (not the headline): fused head forward + backward, batch 8, fp32 ----
     train = None
     if rank == 0 and world == 1 and not args.no_train_step:
@@ -385,12 +390,52 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(B), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": (KERNELS_PER_STEP + (2 if distributed else 0)) * args.steps,  # + round_delta pack / apply
-            "picks_per_image": picks_ok, "train_step": train,
+            "picks_per_image": picks_ok, "other_configs": others, "train_step": train,
             "round_seconds_at_this_rate": round(w["pool_images"] * H * W / (value * 1e6), 4),
         }
         emit(line)
     if distributed:
         dist.destroy_process_group()
+
+
+def run_side_configs(feat, gt, st, dev):
+    """Side measurements (not the headline), 5 steps each after 2 warm-up steps, inputs resident:
+    (a) the reference's default per-round budget BUDGET/len(SELECT_ITER) = 1 % -> 911 picks per image (build.py:78);
+    (b) BASELINE.json configs[3], SYNTHIA->Cityscapes-shaped: 16 classes, 5x5 regions (radius_K=2), 2.2 % budget."""
+    import halo_b200
+    from halo_b200 import synth
+
+    w = WORKLOAD
+    B, C, H, W = feat.shape
+    out = []
+    cases = [("reference default budget: 5 %% over 5 rounds = 911 picks/img, 19 classes, 3x3", w["O"],
+              halo_b200.AcquisitionConfig(num_classes=w["O"], curvature=w["curvature"], radius_k=1, mask_radius_k=w["mask_radius_k"],
+                                          budget=w["budget"], n_rounds=5, uncertainty="entropy", purity="radius", normalize=True)),
+             ("BASELINE.json configs[3] SYNTHIA-shaped: 16 classes, 5x5 regions, 2.2 %% budget = 721 picks/img", 16,
+              halo_b200.AcquisitionConfig(num_classes=16, curvature=w["curvature"], radius_k=2, mask_radius_k=w["mask_radius_k"],
+                                          budget=0.022, n_rounds=1, uncertainty="entropy", purity="radius", normalize=True))]
+    for name, O, cfg in cases:
+        P, A = synth.head_params(O, C, seed=0, device=dev)
+        g = gt if O == w["O"] else torch.where(gt == 255, gt, gt % O)
+
+        def step():
+            st["active"].zero_(); st["selected"].zero_(); st["active_mask"].fill_(255)
+            return halo_b200.acquire_batch(feat, P, A, cfg, g, st["active"], st["selected"], st["active_mask"])
+
+        for _ in range(2):
+            res = step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            res = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out.append({"workload": name % (), "ms_per_step": round(ms, 3), "Mpixel/s": round(B * H * W / ms / 1e3, 1),
+                    "picks_per_image": int(res["n_picked"].min().item()), "images_per_step": B,
+                    "note": "includes the three state-plane resets per step"})
+    return out
 
 
 def run_train_step(feat8, P, A, c, peak):
@@ -506,6 +551,7 @@ def main():
     ap.add_argument("--e2e-batch", type=int, default=4, help="images per end-to-end step (pinned host memory)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the configs[4] fwd+bwd side measurement")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip the 911-pick and configs[3] side measurements")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":
