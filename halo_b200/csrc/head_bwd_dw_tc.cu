@@ -35,8 +35,12 @@ constexpr int DW_UNIT_CHUNKS = HALO_DW_UNIT_CHUNKS;   // consecutive chunks per 
 constexpr int DW_DRAIN = 16;                 // units per accumulator chain
 constexpr int DW_TC_THREADS = 512;
 constexpr int DW_U_BOX_BYTES = 128 * DW_CHUNK * 4;   // 16 KB: one channel block of one chunk
-constexpr int DW_A_COL = 0;                  // A half-buffers: [wg][h] x 32 columns (16 hi + 16 lo)
-constexpr int DW_ACC_COL = 128;              // accumulators: [wg] x (main NP | corr NP)
+#ifndef HALO_DW_NBUF
+#define HALO_DW_NBUF 2
+#endif
+constexpr int DW_NBUF = HALO_DW_NBUF;        // A buffers per channel block, used round-robin by 16-pixel hand-over
+constexpr int DW_A_COL = 0;                  // A buffers: [wg][DW_NBUF] x 32 columns (16 hi + 16 lo)
+constexpr int DW_ACC_COL = 2 * DW_NBUF * 32; // accumulators: [wg] x (main NP | corr NP)
 
 struct DwTcArgs {
   float* dw_part;   // [grid][NR][CP]
@@ -71,11 +75,11 @@ head_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_c
   uint64_t* full = bars;               // [8]  TMA bytes landed
   uint64_t* empty = bars + 8;          // [8]  converters have read the features, MMAs have read G
   uint64_t* g_ready = bars + 16;       // [8]  splitter has written G hi / lo
-  uint64_t* a_full = bars + 24;        // [2][2]
-  uint64_t* a_empty = bars + 28;       // [2][2]
-  uint64_t* acc_full = bars + 32;      // [2]
-  uint64_t* acc_empty = bars + 34;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+  uint64_t* a_full = bars + 24;                      // [2][DW_NBUF]
+  uint64_t* a_empty = a_full + 2 * DW_NBUF;          // [2][DW_NBUF]
+  uint64_t* acc_full = a_empty + 2 * DW_NBUF;        // [2]
+  uint64_t* acc_empty = acc_full + 2;                // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -84,7 +88,7 @@ head_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_c
       mbar_init(&empty[s], 4 * nwg + nwg);   // one lane per converter warp + one tcgen05.commit per MMA issuer
       mbar_init(&g_ready[s], 4);
     }
-    for (int i = 0; i < 4; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2 * DW_NBUF; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -145,9 +149,11 @@ head_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_c
           const uint32_t g_hi = ring_u32 + (uint32_t)(s * stage_bytes) + (uint32_t)(nwg * DW_U_BOX_BYTES), g_lo = g_hi + (uint32_t)a.g_bytes;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(&a_full[g * 2 + h], (uint32_t)ca & 1u);
+            const long long hc = ca * 2 + h;                    // hand-over counter -> buffer, phase
+            const int bf = (int)(hc % DW_NBUF);
+            mbar_wait(&a_full[g * DW_NBUF + bf], (uint32_t)(hc / DW_NBUF) & 1u);
             tc_fence_after();
-            const uint32_t a_col = tb + DW_A_COL + (g * 2 + h) * 32;
+            const uint32_t a_col = tb + DW_A_COL + (g * DW_NBUF + bf) * 32;
             if (elect_one_sync()) {
 #pragma unroll
               for (int ks = 0; ks < 2; ++ks) {
@@ -159,7 +165,7 @@ head_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_c
                 tc_mma_tf32_ts(d_corr, a_col + 16 + ks * 8, b_hi, idesc, first);
                 tc_mma_tf32_ts(d_corr, a_col + ks * 8, b_lo, idesc, 1u);
               }
-              tc_commit(&a_empty[g * 2 + h]);
+              tc_commit(&a_empty[g * DW_NBUF + bf]);
               if (h == 1) tc_commit(&empty[s]);
             }
             __syncwarp();
@@ -193,7 +199,9 @@ head_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_c
           for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(row + (((j ^ (ch & 7))) << 4));
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            mbar_wait(&a_empty[g * 2 + h], ((uint32_t)ca & 1u) ^ 1u);
+            const long long hc = ca * 2 + h;
+            const int bf = (int)(hc % DW_NBUF);
+            mbar_wait(&a_empty[g * DW_NBUF + bf], ((uint32_t)(hc / DW_NBUF) & 1u) ^ 1u);
             tc_fence_after();
             uint32_t hi[16], lo[16];
 #pragma unroll
@@ -209,14 +217,14 @@ head_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_u, const __grid_c
               asm("mov.b64 {%0, %1}, %2;" : "=r"(lo[4 * j + 0]), "=r"(lo[4 * j + 1]) : "l"(l01));
               asm("mov.b64 {%0, %1}, %2;" : "=r"(lo[4 * j + 2]), "=r"(lo[4 * j + 3]) : "l"(l23));
             }
-            const uint32_t taddr = tmem_base + lane_addr + DW_A_COL + (g * 2 + h) * 32;
+            const uint32_t taddr = tmem_base + lane_addr + DW_A_COL + (g * DW_NBUF + bf) * 32;
             tmem_st_x16(taddr, hi);
             tmem_st_x16(taddr + 16, lo);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              mbar_arrive(&a_full[g * 2 + h]);
+              mbar_arrive(&a_full[g * DW_NBUF + bf]);
               if (h == 1) mbar_arrive(&empty[s]);   // this warp's rows of the stage are in registers / TMEM
             }
           }
@@ -346,7 +354,7 @@ int head_bwd_dw_tc_launch(const float* feat, const float* G, float* dw_part, int
   int stages = (int)(((size_t)227 * 1024 - 1024) / stage);
   if (stages > 8) stages = 8;
   a.stages = stages;
-  const size_t smem = (size_t)stages * stage + 37 * 8 + 16;
+  const size_t smem = (size_t)stages * stage + (24 + 4 * DW_NBUF + 4 + 1) * 8 + 16;
   switch (OP) {
     case 4: return launch_dw_tc<16, 4>(tu, tg, a, smem, grid, st);
     case 8: return launch_dw_tc<16, 8>(tu, tg, a, smem, grid, st);
