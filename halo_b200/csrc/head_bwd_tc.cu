@@ -15,9 +15,12 @@
 //   warps 4-7    converters: u -> (hi, lo) -> TMEM, |u|^2
 //   warps 8-11   derivative warps: S,T from TMEM four classes at a time (a ROLLED loop: the fully unrolled 20-class
 //                body was 128 KB of SASS and ran at IPC 0.15 on instruction-cache misses), dlogits -> gS, gT, alpha,
-//                class scalars; G -> TMEM (+ fp32 planes for K4b)
-//   warps 12-15  output warps: D2 from TMEM, + alpha*u (u re-read with one channel group of loads in flight), store du
-// The weight gradient dW = G^T.U (K4b) and the finalisation (K4c) stay in head_bwd.cu.
+//                class scalars; G -> TMEM (+ fp32 planes for K4b); then the output pass of the lower quarter of the
+//                channels of the same tile
+//   warps 12-15  output warps: D2 from TMEM, + alpha*u (u re-read, two channel groups of loads in flight), store du for
+//                the upper three quarters of the channels
+// Control warps run warp-wide and predicate the TMA / tcgen05 instructions on an elected lane (tc_common.cuh).
+// The weight gradient dW = G^T.U is K4b (head_bwd_dw_tc.cu); the finalisation (K4c) stays in head_bwd.cu.
 #include <cuda.h>
 #include <stdlib.h>
 

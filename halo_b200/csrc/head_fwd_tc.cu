@@ -7,7 +7,7 @@
 //        D += U_hi.W_hi + U_lo.W_hi + U_hi.W_lo            (the dropped lo.lo term is ~2^-22 relative)
 //
 // Pipeline of one persistent CTA (one per SM, 512 threads):
-//   warps 0, 2        TMA producers (1 lane each, one per pixel warpgroup): [32 channels x 128 pixels] fp32 boxes of
+//   warps 0, 2        TMA producers (warp-wide loop, TMA on an elected lane; one per pixel warpgroup): [32 channels x 128 pixels] fp32 boxes of
 //                     the NCHW feature tensor (viewed as a 2-D [N*C, H*W] tensor) into that warpgroup's 3-deep
 //                     shared-memory ring (16 KB per stage), completion by mbarrier tx-count.
 //   warps 4-7, 8-11   two CONVERTER warpgroups working on alternate (adjacent) 128-pixel tiles; thread = pixel = TMEM
@@ -17,7 +17,7 @@
 //                     the same register epilogue as the CUDA-core kernel (Mobius algebra, asinh, radius, softmax
 //                     entropy); the converters never wait for it (profiles/r1_k1_tc.md: a warpgroup that converts AND
 //                     finishes its tile leaves the SM issue slots half empty).
-//   warps 1, 3        MMA issuers (1 lane each, one per pixel warpgroup): tcgen05.mma.kind::tf32, M=128 (pixels) x
+//   warps 1, 3        MMA issuers (warp-wide loop, tcgen05 on an elected lane; one per pixel warpgroup): tcgen05.mma.kind::tf32, M=128 (pixels) x
 //                     N=NP (2*OP padded to 16) x K=8,
 //                     A from TMEM, B (class parameters, hi and lo planes) from shared memory, D in TMEM;
 //                     tcgen05.commit releases A buffers / publishes accumulators through mbarriers.

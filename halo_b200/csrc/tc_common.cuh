@@ -205,12 +205,6 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor, MN-major, no swizzle: T=4 elements contiguous along MN, MN groups SBO apart,
-// K elements 16 B apart, groups of 8 K elements LBO apart (CUTLASS make_umma_desc<Major::MN>, INTERLEAVE)
-__device__ __forceinline__ uint64_t make_b_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return make_b_desc(smem_addr, lbo_bytes, sbo_bytes);  // same bit fields; the major-ness lives in the instruction descriptor
-}
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
