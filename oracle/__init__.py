@@ -15,6 +15,8 @@ function by function, each citing the reference file:line it follows
 * ``score``        -- ``core/active/floating_region.py:12-23,26-217``.
 * ``select``       -- ``core/active/build.py:27-64`` (sequential greedy arg-max selection).
 * ``acquire``      -- ``core/active/build.py:71-160`` minus model forward / file I/O.
+* ``delta``        -- ``core/active/build.py:45-48,58-62``: the window labelling of a round, as exchanged between
+  image shards by ``halo_round_delta_pack`` / ``halo_round_delta_apply``.
 
 Parity pinning: the reference ships no tests, golden vectors or fixtures for this path
 ("parity unpinned" by the reference's own tests).  The oracle is
