@@ -23,7 +23,7 @@ Parity pinning: the reference ships no tests, golden vectors or fixtures for thi
 therefore pinned by running the reference's OWN modules (imported unchanged from the
 reference checkout behind stubs for the absent third-party packages, see
 ``oracle/ref_import.py``) on seeded inputs: ``tests/golden/make_golden.py`` freezes those
-outputs as fixtures under ``tests/golden/`` and ``tests/test_oracle_vs_reference.py``
+outputs as fixtures under ``tests/golden/`` and ``tests/test_oracle_golden.py``
 re-checks the restatement against the live reference whenever the checkout is present.
 The only part that cannot be pinned against real code is the geoopt boundary (geoopt is
 not installed and cannot be fetched); its restatement follows geoopt's published
