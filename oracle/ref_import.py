@@ -2,7 +2,7 @@
 
 Only usable where the checkout exists (this container: /root/reference; never on the GPU box).
 Used by tests/golden/make_golden.py to freeze golden vectors and by
-tests/test_oracle_vs_reference.py to pin the restatement against the live reference.
+tests/test_oracle_golden.py to pin the restatement against the live reference.
 
 The reference imports four packages that are not installed here; they are replaced by the
 smallest stubs that let `core/utils/hyperbolic.py`, `core/active/floating_region.py` and
