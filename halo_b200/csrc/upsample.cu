@@ -6,35 +6,65 @@
 // Here every output pixel interpolates its 4 low-resolution neighbours on the fly and writes the three planes K2 needs
 // (per-pixel uncertainty, label, radius): neither up-sampled tensor is ever materialised.
 //   * logits: fp32 arithmetic with torch's own source-index rule (scale = (in-1)/(out-1) in float, src = scale*dst);
-//   * embedding: float64 throughout, like the reference (1 - c|x|^2 near the ball boundary needs it); for raw features the
-//     exp-map factor gamma of each low-resolution pixel is precomputed once (gamma_lr_kernel), x_nb = gamma_nb * u_nb.
+//   * embedding: float64 throughout, like the reference (1 - c|x|^2 near the ball boundary needs it).  Only the NORM of
+//     the interpolated embedding is needed, and | sum_t w_t x_t |^2 = sum_tt' w_t w_t' <x_t, x_t'>: a pre-pass
+//     (gram_lr_kernel) computes, per low-resolution pixel, its squared norm and the four dot products with / between its
+//     right, lower and lower-right neighbours (plus the exp-map factor gamma for raw features, x_nb = gamma_nb * u_nb);
+//     an output pixel then evaluates a 4x4 quadratic form from 14 cached doubles instead of interpolating C channels
+//     (1 024 fp64 FMAs per output pixel at C = 256).  Algebraically identical to interpolate-then-norm.
 #include "common.cuh"
 #include "head_common.cuh"
 
 namespace halo {
 
-// gamma(u) = tanh(min(s|u|,15), clip 1-1e-5) / (s|u|) per low-resolution pixel, in double
-__global__ void gamma_lr_kernel(const float* __restrict__ u, double* __restrict__ gamma, float c, int C, int hw, long long total) {
+// Per low-resolution pixel p = (y, x), with the clamped neighbours r = (y, x1), d = (y1, x), q = (y1, x1) the output
+// pixels of its cell use (x1 = x + (x < w-1), y1 = y + (y < h-1)):
+//   plane 0  <e_p, e_p>     plane 1  <e_p, e_r>     plane 2  <e_p, e_d>     plane 3  <e_p, e_q>     plane 4  <e_r, e_d>
+//   plane 5  gamma_p = tanh(min(s|u|,15), clip 1-1e-5) / (s|u|) for raw features, 1 for points already on the ball
+// (e = the stored embedding values; the factor gamma is folded into the interpolation weights later).  ws: [N][6][h*w].
+constexpr int UP_WS_PLANES = 6;
+template <typename TE>
+__global__ void gram_lr_kernel(const TE* __restrict__ emb, double* __restrict__ ws, int tangent, float c, int C, int eh, int ew,
+                               long long total) {
+  const int hw = eh * ew;
   const double s = sqrt((double)c);
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x) {
     const long long n = g / hw;
     const int p = (int)(g - n * hw);
-    const float* src = u + (size_t)n * C * hw + p;
-    double n2 = 0.0;
+    const int y = p / ew, x = p - y * ew;
+    const int x1 = x + ((x < ew - 1) ? 1 : 0), y1 = y + ((y < eh - 1) ? 1 : 0);
+    const int jr = y * ew + x1, jd = y1 * ew + x, jq = y1 * ew + x1;
+    const TE* src = emb + (size_t)n * C * hw;
+    double s0 = 0.0, sr = 0.0, sd = 0.0, sq = 0.0, sa = 0.0;
     for (int ch = 0; ch < C; ++ch) {
-      const double v = (double)src[(size_t)ch * hw];
-      n2 = fma(v, v, n2);
+      const TE* row = src + (size_t)ch * hw;
+      const double a = (double)row[p], b = (double)row[jr], d = (double)row[jd], q = (double)row[jq];
+      s0 = fma(a, a, s0);
+      sr = fma(a, b, sr);
+      sd = fma(a, d, sd);
+      sq = fma(a, q, sq);
+      sa = fma(b, d, sa);
     }
-    const double nn = fmax(sqrt(n2), 1e-15);
-    const double t = fmin(tanh(fmin(s * nn, 15.0)), 1.0 - 1e-5);
-    gamma[g] = t / (s * nn);
+    double* out = ws + (size_t)n * UP_WS_PLANES * hw + p;
+    out[0] = s0;
+    out[(size_t)hw] = sr;
+    out[(size_t)2 * hw] = sd;
+    out[(size_t)3 * hw] = sq;
+    out[(size_t)4 * hw] = sa;
+    double gam = 1.0;
+    if (tangent) {
+      const double nn = fmax(sqrt(s0), 1e-15);
+      const double t = fmin(tanh(fmin(s * nn, 15.0)), 1.0 - 1e-5);
+      gam = t / (s * nn);
+    }
+    out[(size_t)5 * hw] = gam;
   }
 }
 
 struct UpArgs {
   const float* logits;   // [N,O,h,w] or NULL
   const void* emb;       // [N,C,h,w] or NULL
-  const double* gamma;   // [N,h,w] (tangent kind) or NULL
+  const double* gram;    // [N,6,eh*ew] from gram_lr_kernel, or NULL
   const uint8_t* gt;     // [N,H,W] or NULL
   float* pixunc;
   uint8_t* label;
@@ -45,7 +75,6 @@ struct UpArgs {
   float c, inv_log19;
 };
 
-template <typename TE>
 __global__ void __launch_bounds__(256) upsample_inputs_kernel(const UpArgs a) {
   const int n = blockIdx.z;
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
@@ -70,29 +99,50 @@ __global__ void __launch_bounds__(256) upsample_inputs_kernel(const UpArgs a) {
         const float* q = L + (size_t)k * hw;
         return hy * (hx * __ldg(q + i00) + lx * __ldg(q + i01)) + ly * (hx * __ldg(q + i10) + lx * __ldg(q + i11));
       };
-      float mx = logit(0);
+      float mx, Z = 0.f, ent = 0.f, eg = 0.f;
       int arg = 0;
-      for (int k = 1; k < a.O; ++k) {
-        const float v = logit(k);
-        if (v > mx) { mx = v; arg = k; }
-      }
-      float Z = 0.f;
-      for (int k = 0; k < a.O; ++k) Z += __expf(logit(k) - mx);
-      const float iz = 1.f / Z;
       const int g8 = (a.gt != nullptr) ? a.gt[pix] : 255;
+      if (a.O <= 32) {
+        // the interpolated logits stay in registers (static indices under full unrolling): one interpolation per class
+        float lg[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) lg[k] = (k < a.O) ? logit(k) : -3.0e38f;
+        mx = lg[0];
+#pragma unroll
+        for (int k = 1; k < 32; ++k)
+          if (k < a.O && lg[k] > mx) { mx = lg[k]; arg = k; }
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          lg[k] = (k < a.O) ? __expf(lg[k] - mx) : 0.f;
+          Z += lg[k];
+        }
+        const float iz0 = 1.f / Z;
+        const int gtf0 = (g8 == 255) ? arg : g8;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float pk = lg[k] * iz0;
+          if (k < a.O) ent -= pk * __logf(pk + 1e-6f);
+          if (k == gtf0) eg = lg[k];
+        }
+      } else {
+        mx = logit(0);
+        for (int k = 1; k < a.O; ++k) {
+          const float v = logit(k);
+          if (v > mx) { mx = v; arg = k; }
+        }
+        for (int k = 0; k < a.O; ++k) Z += __expf(logit(k) - mx);
+        const float iz0 = 1.f / Z;
+        const int gtf0 = (g8 == 255) ? arg : g8;
+        for (int k = 0; k < a.O; ++k) {
+          const float pk = __expf(logit(k) - mx) * iz0;
+          ent -= pk * __logf(pk + 1e-6f);
+        }
+        eg = (gtf0 < a.O) ? __expf(logit(gtf0) - mx) : 0.f;
+      }
+      const float iz = 1.f / Z;
       const int gtf = (g8 == 255) ? arg : g8;
       if (a.pixunc != nullptr) {
-        float v;
-        if (a.pixunc_mode == HALO_PIXUNC_ENTROPY) {
-          float ent = 0.f;
-          for (int k = 0; k < a.O; ++k) {
-            const float pk = __expf(logit(k) - mx) * iz;
-            ent -= pk * __logf(pk + 1e-6f);
-          }
-          v = ent * a.inv_log19;
-        } else {
-          v = (gtf < a.O) ? 1.f - __expf(logit(gtf) - mx) * iz : 1.f;
-        }
+        const float v = (a.pixunc_mode == HALO_PIXUNC_ENTROPY) ? ent * a.inv_log19 : ((gtf < a.O) ? 1.f - eg * iz : 1.f);
         a.pixunc[pix] = v;
       }
       if (a.label != nullptr) a.label[pix] = (uint8_t)((a.label_mode == HALO_LABEL_GT_FILLED) ? gtf : arg);
@@ -109,17 +159,16 @@ __global__ void __launch_bounds__(256) upsample_inputs_kernel(const UpArgs a) {
       const double dly = dfy - (double)ey0, dlx = dfx - (double)ex0;
       double w00 = (1.0 - dly) * (1.0 - dlx), w01 = (1.0 - dly) * dlx, w10 = dly * (1.0 - dlx), w11 = dly * dlx;
       const int j00 = ey0 * a.ew + ex0, j01 = ey0 * a.ew + ex1, j10 = ey1 * a.ew + ex0, j11 = ey1 * a.ew + ex1;
-      if (a.gamma != nullptr) {  // raw features: fold the exp-map factor of each neighbour into its weight
-        const double* G = a.gamma + (size_t)n * hw;
-        w00 *= G[j00]; w01 *= G[j01]; w10 *= G[j10]; w11 *= G[j11];
-      }
-      const TE* E = reinterpret_cast<const TE*>(a.emb) + (size_t)n * a.C * hw;
-      double n2 = 0.0;
-      for (int ch = 0; ch < a.C; ++ch) {
-        const TE* q = E + (size_t)ch * hw;
-        const double v = w00 * (double)q[j00] + w01 * (double)q[j01] + w10 * (double)q[j10] + w11 * (double)q[j11];
-        n2 = fma(v, v, n2);
-      }
+      const double* G0 = a.gram + (size_t)n * UP_WS_PLANES * hw;
+      const double *GR = G0 + hw, *GD = G0 + (size_t)2 * hw, *GQ = G0 + (size_t)3 * hw, *GA = G0 + (size_t)4 * hw,
+                   *GAM = G0 + (size_t)5 * hw;
+      // raw features: fold the exp-map factor of each neighbour into its weight (1 for points already on the ball)
+      w00 *= GAM[j00]; w01 *= GAM[j01]; w10 *= GAM[j10]; w11 *= GAM[j11];
+      // | w00 e00 + w01 e01 + w10 e10 + w11 e11 |^2 from the cell's Gram entries (j01 = right, j10 = lower, j11 = lower-right)
+      double n2 = w00 * w00 * G0[j00] + w01 * w01 * G0[j01] + w10 * w10 * G0[j10] + w11 * w11 * G0[j11];
+      n2 += 2.0 * (w00 * w01 * GR[j00] + w10 * w11 * GR[j10] + w00 * w10 * GD[j00] + w01 * w11 * GD[j01] +
+                   w00 * w11 * GQ[j00] + w01 * w10 * GA[j00]);
+      n2 = fmax(n2, 0.0);
       float r;
       if (a.norm_mode == HALO_NORM_EUCLID) {
         r = (float)sqrt(n2);
@@ -156,7 +205,7 @@ __global__ void up_stats_init_kernel(float* stats, int N) {
 using namespace halo;
 
 extern "C" size_t halo_upsample_workspace_bytes(int N, int h, int w) {
-  return (N > 0 && h > 0 && w > 0) ? (size_t)N * h * w * sizeof(double) : 0;
+  return (N > 0 && h > 0 && w > 0) ? (size_t)N * UP_WS_PLANES * h * w * sizeof(double) : 0;
 }
 
 extern "C" int halo_upsample_score_inputs(const float* logits_lr, const void* emb_lr, int emb_kind, float c,
@@ -176,22 +225,26 @@ extern "C" int halo_upsample_score_inputs(const float* logits_lr, const void* em
   HALO_CHECK_ARG(H <= 65535 && N <= 65535, "halo_upsample_score_inputs: grid too large");
   cudaStream_t st = (cudaStream_t)stream;
   UpArgs a;
-  a.logits = logits_lr; a.emb = emb_lr; a.gamma = nullptr; a.gt = gt; a.pixunc = pixunc; a.label = label; a.radius = radius;
+  a.logits = logits_lr; a.emb = emb_lr; a.gram = nullptr; a.gt = gt; a.pixunc = pixunc; a.label = label; a.radius = radius;
   a.stats = stats; a.emb_kind = emb_kind; a.pixunc_mode = pixunc_mode; a.label_mode = label_mode; a.norm_mode = norm_mode;
   a.N = N; a.O = O; a.C = C; a.lh = lh; a.lw = lw; a.eh = eh; a.ew = ew; a.H = H; a.W = W; a.c = c; a.inv_log19 = (float)(1.0 / log(19.0));
-  if (emb_lr && emb_kind == HALO_FEAT_TANGENT_F32) {
+  if (emb_lr) {
     const size_t need = halo_upsample_workspace_bytes(N, eh, ew);
     if (!ws || ws_bytes < need) {
       set_error("halo_upsample_score_inputs: workspace %zu < %zu bytes", ws_bytes, need);
       return HALO_ERR_WORKSPACE;
     }
     const long long total = (long long)N * eh * ew;
-    long long blocks = (total + 255) / 256;
-    if (blocks > (long long)sm_count() * 8) blocks = (long long)sm_count() * 8;
-    gamma_lr_kernel<<<(int)blocks, 256, 0, st>>>((const float*)emb_lr, (double*)ws, c, C, eh * ew, total);
-    int rc = launch_status("gamma_lr_kernel");
+    long long blocks = (total + 127) / 128;
+    if (blocks > (long long)sm_count() * 16) blocks = (long long)sm_count() * 16;
+    if (emb_kind == HALO_FEAT_BALL_F64)
+      gram_lr_kernel<double><<<(int)blocks, 128, 0, st>>>((const double*)emb_lr, (double*)ws, 0, c, C, eh, ew, total);
+    else
+      gram_lr_kernel<float><<<(int)blocks, 128, 0, st>>>((const float*)emb_lr, (double*)ws, emb_kind == HALO_FEAT_TANGENT_F32, c, C,
+                                                        eh, ew, total);
+    int rc = launch_status("gram_lr_kernel");
     if (rc) return rc;
-    a.gamma = (const double*)ws;
+    a.gram = (const double*)ws;
   }
   if (stats) {
     up_stats_init_kernel<<<(N + 255) / 256, 256, 0, st>>>(stats, N);
@@ -199,7 +252,6 @@ extern "C" int halo_upsample_score_inputs(const float* logits_lr, const void* em
     if (rc) return rc;
   }
   dim3 grid((W + 255) / 256, H, N);
-  if (emb_lr && emb_kind == HALO_FEAT_BALL_F64) upsample_inputs_kernel<double><<<grid, 256, 0, st>>>(a);
-  else upsample_inputs_kernel<float><<<grid, 256, 0, st>>>(a);
+  upsample_inputs_kernel<<<grid, 256, 0, st>>>(a);
   return launch_status("upsample_inputs_kernel");
 }

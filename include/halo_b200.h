@@ -123,7 +123,8 @@ int halo_logits_stats(const float* logits, const uint8_t* gt, int pixunc_mode, i
  *   logits_lr [N,O,lh,lw] f32 | NULL;  emb_lr [N,C,eh,ew] per emb_kind (halo_feat_kind: raw features get
  *   expmap0+project at the low-resolution pixels first) | NULL -- the two may come at different resolutions (the
  *   DeepLab v3+ head up-samples only its logits, classifier.py:556-557);  outputs at [N,H,W]: pixunc f32, label u8,
- *   radius f32, stats [N,4].  ws: halo_upsample_workspace_bytes(N,eh,ew) (only read for HALO_FEAT_TANGENT_F32). */
+ *   radius f32, stats [N,4].  ws: halo_upsample_workspace_bytes(N,eh,ew), required whenever emb_lr is given (it holds the
+ *   per-low-resolution-pixel Gram entries and exp-map factors the output pixels evaluate the norm from). */
 size_t halo_upsample_workspace_bytes(int N, int h, int w);
 int halo_upsample_score_inputs(const float* logits_lr, const void* emb_lr, int emb_kind, float c, const uint8_t* gt,
                                int pixunc_mode, int label_mode, int norm_mode, float* pixunc, uint8_t* label,
