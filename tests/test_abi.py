@@ -52,6 +52,12 @@ def test_bad_arguments_return_status_not_crash():
     assert rc == nat.ERR_WORKSPACE
     rc = lib.halo_score(one, one, None, None, None, 0, 0, 1, 4, 3, 19, one, None, one, 1, 8, 8, one, 64, None)
     assert rc == nat.ERR_BAD_ARG and "odd" in nat.last_error()
+    rc = lib.halo_round_delta_pack(None, one, one, one, 1, 4, 8, 8, 1, None)
+    assert rc == nat.ERR_BAD_ARG and "halo_round_delta_pack" in nat.last_error()
+    rc = lib.halo_round_delta_apply(one, one, one, one, one, 1, 0, 8, 8, 1, None)
+    assert rc == nat.ERR_BAD_ARG and "halo_round_delta_apply" in nat.last_error()
+    rc = lib.halo_upsample_score_inputs(None, one, 0, 1.0, None, 0, 0, 0, None, None, one, None, 1, 0, 8, 0, 0, 4, 4, 8, 8, None, 0, None)
+    assert rc == nat.ERR_WORKSPACE   # an embedding always needs the Gram workspace
     rc = lib.halo_select_f32(one, one, one, one, one, -1, 1, 5, 0, one, None, 1, 8, 8, one, 1 << 20, None)
     assert rc == nat.ERR_BAD_ARG
     with pytest.raises(ValueError):
