@@ -151,7 +151,8 @@ def test_backward_matches_golden(golden):
 
 
 @pytest.mark.parametrize("shape", [(19, 64, 24, 40, 2, 0.1), (19, 256, 16, 24, 1, 0.1), (16, 128, 20, 20, 2, 0.3),
-                                   (19, 256, 130, 126, 1, 0.1), (5, 32, 9, 12, 3, 1.0), (24, 96, 16, 16, 1, 0.2)])
+                                   (19, 256, 130, 126, 1, 0.1), (5, 32, 9, 12, 3, 1.0), (24, 96, 16, 16, 1, 0.2),
+                                   (19, 160, 20, 24, 2, 0.1), (8, 224, 12, 20, 1, 0.2)])
 def test_backward_tensor_core_pixel_pass(shape, monkeypatch):
     """K4a on the tensor cores (two chained tcgen05 GEMMs) against fp64
     autograd through the oracle and against the fp32 CUDA-core pixel pass."""
