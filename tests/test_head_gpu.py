@@ -235,3 +235,20 @@ def test_backward_full_size_tensor_core_vs_cuda_core(shape, monkeypatch):
     assert rel_err(du, du_cc) <= 1e-4
     assert rel_err(dP, dP_cc) <= 1e-4
     assert rel_err(dA, dA_cc) <= 1e-4
+
+
+@pytest.mark.parametrize("shape", [(19, 256, 2, 2, 1), (19, 128, 2, 4, 3), (19, 256, 4, 4, 37), (3, 64, 2, 2, 5),
+                                   (19, 256, 1, 132, 2), (16, 128, 2, 2, 300)])
+def test_tiny_planes_forward_and_backward(shape):
+    """Planes much smaller than a TMA box (128-pixel tiles, 32-pixel chunks of the weight-gradient kernel), a single live
+    pixel row per tile, hundreds of images: the tensor-core forward and both tensor-core backward kernels against fp64."""
+    O, C, H, W, N = shape
+    P, A = synth.head_params(O, C, seed=1, dtype=torch.float64)
+    u = torch.stack([synth.image_features(i, C, H, W, sigma=0.1) for i in range(N)])
+    dl = torch.randn((N, O, H, W), generator=torch.Generator().manual_seed(1)) * 1e-3
+    du_ref, dP_ref, dA_ref = ohead.head_grads(u, P, A, dl, 1.0)
+    logits_ref, _, _ = ohead.head_forward(u, P, A, 1.0)
+    args = (u.to(DEV), P.to(DEV), A.to(DEV), 1.0)
+    assert rel_err(halo_b200.head_forward(*args, want_logits=True)["logits"], logits_ref) <= TOL
+    du, dP, dA = halo_b200.head_backward(*args, dl.to(DEV))
+    assert rel_err(du, du_ref) <= 1e-4 and rel_err(dP, dP_ref) <= 1e-4 and rel_err(dA, dA_ref) <= 1e-4
