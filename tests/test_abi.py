@@ -88,3 +88,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/halo_b200.h compiles as C99 and as C++17 on its own (no torch / CUDA types)."""
+    import shutil
+    import subprocess
+
+    hdr = os.path.join(ROOT, "include", "halo_b200.h")
+    for cc, args in (("gcc", ["-std=c99", "-x", "c"]), ("g++", ["-std=c++17", "-x", "c++"])):
+        exe = shutil.which(cc)
+        if exe is None:
+            pytest.skip("%s not installed" % cc)
+        r = subprocess.run([exe, "-fsyntax-only", "-Wall", "-Wextra", "-Werror"] + args + [hdr], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    text = open(hdr).read()
+    assert "at::Tensor" not in text and "#include <torch" not in text   # plain pointers and sizes only
