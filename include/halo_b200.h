@@ -98,7 +98,10 @@ int halo_head_fwd(const void* feat, int feat_kind, const float* P, const float* 
 
 /* ---- head backward (core/train_learners.py:238,362,457,557: autograd through expmap + HyperMLR) ----
  *   feat [N,C,H,W] f32 raw features (HALO_FEAT_TANGENT_F32) ; dlogits [N,O,H,W] f32
- *   dfeat [N,C,H,W] f32 ; dP, dA [O,C] f32 (overwritten, not accumulated) */
+ *   dfeat [N,C,H,W] f32 ; dP, dA [O,C] f32 (overwritten, not accumulated)
+ * Tensor-core kernels (tcgen05) run when C % 32 == 0, 64 <= C <= 256, O <= 24, H*W % 4 == 0 (weight gradient: C = 128 or
+ * 256); other shapes take the fp32 CUDA-core kernels.  Reductions have a fixed order: results are bitwise reproducible
+ * on a given device.  Environment knobs for A/B tests: HALO_BWD_CUDA_CORE=1, HALO_BWD_DW_CUDA_CORE=1 pin the fp32 paths. */
 size_t halo_head_bwd_workspace_bytes(int N, int C, int O, int H, int W);
 int halo_head_bwd(const float* feat, const float* P, const float* A, float c, const float* dlogits,
                   float* dfeat, float* dP, float* dA, int N, int C, int O, int H, int W,
