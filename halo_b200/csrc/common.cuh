@@ -11,6 +11,8 @@ namespace halo {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* where);
+void note_path(int bits, bool reset);                          // halo_last_path(): which kernel variant the last head call took
+void warn_slow_path_once(int reason, const char* fmt, ...);    // one stderr line per process and reason
 
 #define HALO_CHECK_ARG(cond, ...)                 \
   do {                                            \

@@ -471,13 +471,18 @@ extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, 
     rc = head_pack_tc_launch(wpack, wtc, C, CPAD, O, st);
     if (rc) return rc;
     cls_grid = head_bwd_tc_grid(N, HW);
+    note_path(HALO_PATH_BWD_PIX_TC, true);
     rc = head_bwd_tc_launch(feat, dlogits, dfeat, G, cls_part, wpack, wtc, w2, c, N, C, O, H, W, cls_grid, st);
     if (rc) return rc;
     const char* force_dw = getenv("HALO_BWD_DW_CUDA_CORE");  // parity tests pin the fp32 CUDA-core weight-gradient GEMM
     if (!(force_dw && force_dw[0] == '1') && head_bwd_dw_tc_supported(C, O, H, W, feat, G)) {
       dw_grid = head_bwd_dw_tc_grid(N, HW);
+      note_path(HALO_PATH_BWD_DW_TC, false);
       rc = head_bwd_dw_tc_launch(feat, G, dw_part, N, C, O, H, W, CP, dw_grid, st);
     } else {
+      note_path(HALO_PATH_BWD_DW_CUDA_CORE, false);
+      if (!(force_dw && force_dw[0] == '1') && (long long)N * HW >= (1 << 16))
+        warn_slow_path_once(2, "halo_head_bwd weight gradient N=%d C=%d O=%d H=%d W=%d runs on the fp32 CUDA cores", N, C, O, H, W);
       const long long units = (long long)N * ((HW + DW_PX - 1) / DW_PX);
       switch (OP) {
         case 4: head_bwd_dw_kernel<4><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
@@ -485,11 +490,18 @@ extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, 
         case 12: head_bwd_dw_kernel<12><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
         case 16: head_bwd_dw_kernel<16><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
         case 20: head_bwd_dw_kernel<20><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
-        default: head_bwd_dw_kernel<24><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+        case 24: head_bwd_dw_kernel<24><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+        case 28: head_bwd_dw_kernel<28><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+        case 32: head_bwd_dw_kernel<32><<<dw_grid, DW_THREADS, 0, st>>>(feat, G, dw_part, N, C, HW, cblocks, units); break;
+        default: set_error("halo_head_bwd: padded class count %d has no weight-gradient kernel", OP); return HALO_ERR_UNSUPPORTED;
       }
       rc = launch_status("head_bwd_dw_kernel");
     }
   } else {
+    note_path(HALO_PATH_BWD_PIX_CUDA_CORE | HALO_PATH_BWD_DW_CUDA_CORE, true);
+    if (!(force_cc && force_cc[0] == '1') && (long long)N * HW >= (1 << 16))
+      warn_slow_path_once(1, "halo_head_bwd N=%d C=%d O=%d H=%d W=%d runs on the fp32 CUDA cores (tensor-core path needs "
+                          "C %% 32 == 0, 64 <= C <= 256, O <= 24, H*W %% 4 == 0)", N, C, O, H, W);
     switch (OP) {
       case 4: rc = launch_bwd<4>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;
       case 8: rc = launch_bwd<8>(a, vec, smem, pix_grid, dw_grid, feat, dw_part, cblocks, st); break;

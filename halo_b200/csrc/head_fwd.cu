@@ -333,8 +333,13 @@ extern "C" int halo_head_fwd(const void* feat, int feat_kind, const float* P, co
 #endif
   if (use_tc) {
     float* wtc = (float*)((unsigned char*)ws + (smem + 255) / 256 * 256);
+    note_path(HALO_PATH_FWD_TC, true);
     return head_fwd_tc_launch(a, (const float*)ws, wtc, st);
   }
+  note_path(HALO_PATH_FWD_CUDA_CORE, true);
+  if (!no_tc && feat_kind == HALO_FEAT_TANGENT_F32 && (long long)N * H * W >= (1 << 16))
+    warn_slow_path_once(0, "halo_head_fwd N=%d C=%d O=%d H=%d W=%d runs on the fp32 CUDA cores (tensor-core path needs "
+                        "C %% 32 == 0, C <= 256, H*W %% 4 == 0, 16-byte aligned features)", N, C, O, H, W);
   const size_t esz = (feat_kind == HALO_FEAT_BALL_F64) ? 8 : 4;
   bool vec = (a.HW % 2 == 0) && (((uintptr_t)feat) % (2 * esz) == 0);
   if (logits && ((uintptr_t)logits % 8)) vec = false;

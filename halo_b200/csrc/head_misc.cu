@@ -78,6 +78,54 @@ __global__ void ball_norm_kernel(const TIN* __restrict__ x, float* __restrict__ 
   }
 }
 
+// fp64 radius plane + per-image fp64 extrema for the "hyper" purity (floating_region.py:94-110): the reference
+// quantises an fp64 radius into K bins with round-half-even, so an fp32 radius flips bins at ~1e-4 of the pixels; the bins
+// only match when the radius is formed the way the reference forms it, from an fp64 |u|^2 (tangent features: closed form
+// of expmap0 + project + dist0) or an fp64 |x|^2 (points already on the ball).  Radii are >= 0, so their bit patterns
+// order like unsigned integers and 64-bit integer atomics give the extrema.
+template <typename TIN>
+__global__ void radius64_kernel(const TIN* __restrict__ x, double* __restrict__ out, unsigned long long* __restrict__ stats,
+                                int tangent, double c, int C, int HW, int blocks_per_img) {
+  const int n = blockIdx.x / blocks_per_img;
+  const int p = (blockIdx.x - n * blocks_per_img) * blockDim.x + threadIdx.x;
+  unsigned long long lo = 0x7ff0000000000000ull, hi = 0ull;
+  if (p < HW) {
+    const TIN* src = x + (size_t)n * C * HW + p;
+    double n2 = 0.0;
+    for (int ch = 0; ch < C; ++ch) {
+      const double v = (double)src[(size_t)ch * HW];
+      n2 = fma(v, v, n2);
+    }
+    const double s = sqrt(c);
+    double t;
+    if (tangent) {
+      const double nn = fmax(sqrt(n2), 1e-15);
+      t = fmin(tanh(fmin(s * nn, 15.0)), 1.0 - 1e-5);   // s*|x| after expmap0 + project (fp64 eps 1e-5)
+    } else {
+      t = fmin(s * sqrt(n2), 1.0 - 1e-7);                // geoopt artan_k clamp (hyperbolic.py:83)
+    }
+    const double r = (log1p(t) - log1p(-t)) / s;         // 2 artanh(t) / s
+    out[(size_t)n * HW + p] = r;
+    lo = hi = (unsigned long long)__double_as_longlong(r);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo, o), h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+    lo = l2 < lo ? l2 : lo;
+    hi = h2 > hi ? h2 : hi;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(stats + 2 * n + 0, lo);
+    atomicMax(stats + 2 * n + 1, hi);
+  }
+}
+
+__global__ void stats64_init_kernel(unsigned long long* stats, int N) {
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    stats[2 * n + 0] = 0x7ff0000000000000ull;  // +inf
+    stats[2 * n + 1] = 0ull;
+  }
+}
+
 __global__ void stats_init_kernel(float* stats, int N) {
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
     stats[4 * n + 0] = __int_as_float(0x7f800000);
@@ -162,6 +210,26 @@ extern "C" int halo_ball_norm(const void* x, int x_f64, float c, int norm_mode, 
   else
     ball_norm_kernel<float><<<bpi * N, MISC_THREADS, 0, st>>>((const float*)x, out, stats, hc, norm_mode, C, HW, bpi);
   return launch_status("ball_norm_kernel");
+}
+
+extern "C" int halo_radius_f64(const void* feat, int feat_kind, float c, double* radius64, double* stats64, int N, int C,
+                               int H, int W, halo_stream_t stream) {
+  HALO_CHECK_ARG(feat && radius64 && stats64, "halo_radius_f64: NULL pointer");
+  HALO_CHECK_ARG(N > 0 && C > 0 && H > 0 && W > 0 && c > 0.f, "halo_radius_f64: bad dims / curvature");
+  HALO_CHECK_ARG(feat_kind >= 0 && feat_kind <= 2, "halo_radius_f64: bad feat_kind");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W;
+  const int bpi = (HW + MISC_THREADS - 1) / MISC_THREADS;
+  unsigned long long* s64 = reinterpret_cast<unsigned long long*>(stats64);
+  stats64_init_kernel<<<(N + 255) / 256, 256, 0, st>>>(s64, N);
+  int rc = launch_status("stats64_init_kernel");
+  if (rc) return rc;
+  if (feat_kind == HALO_FEAT_BALL_F64)
+    radius64_kernel<double><<<bpi * N, MISC_THREADS, 0, st>>>((const double*)feat, radius64, s64, 0, (double)c, C, HW, bpi);
+  else
+    radius64_kernel<float><<<bpi * N, MISC_THREADS, 0, st>>>((const float*)feat, radius64, s64,
+                                                              feat_kind == HALO_FEAT_TANGENT_F32, (double)c, C, HW, bpi);
+  return launch_status("radius64_kernel");
 }
 
 extern "C" int halo_logits_stats(const float* logits, const uint8_t* gt, int pixunc_mode, int label_mode, float* pixunc,

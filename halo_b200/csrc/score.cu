@@ -15,6 +15,8 @@ struct ScoreArgs {
   const float* pixunc;
   const float* radius;
   const float* radius_stats;
+  const double* radius64;        // fp64 radius plane + {min,max} per image: the "hyper" bins follow the reference's
+  const double* radius_stats64;  // fp64 arithmetic when given (floating_region.py:94-110)
   const uint8_t* label;
   const uint8_t* active;
   float* score;
@@ -43,6 +45,14 @@ __device__ __forceinline__ int radius_bin(float r, float rmin, float rmax, int K
   return (int)rintf(b);  // round half to even, like torch.round
 }
 
+// the same in the reference's own precision: fp64 radius, fp64 extrema (python floats), torch.round on doubles
+__device__ __forceinline__ int radius_bin64(double r, double rmin, double rmax, int K) {
+  const double x = (r - rmin) / (rmax - rmin);
+  double b = (1.0 - x) * (double)K - 0.5;
+  b = fmin(fmax(b, -0.5 + 1e-5), (double)K - 0.5 - 1e-5);
+  return (int)rint(b);
+}
+
 __global__ void __launch_bounds__(SC_THREADS) score_pass_a_kernel(const ScoreArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int ru = (a.unc_mode == HALO_UNC_BOXSUM) ? a.k / 2 : 0;
@@ -61,7 +71,12 @@ __global__ void __launch_bounds__(SC_THREADS) score_pass_a_kernel(const ScoreArg
   if (threadIdx.x < 8) s_present[threadIdx.x] = 0u;
   if (threadIdx.x < 4) s_mm[threadIdx.x] = (threadIdx.x & 1) ? 0u : 0xffffffffu;
   float rmin = 0.f, rmax = 1.f;
-  if (a.pur_mode == HALO_PUR_RADIUS_BINS) {
+  double rmin64 = 0.0, rmax64 = 1.0;
+  const bool bins64 = (a.pur_mode == HALO_PUR_RADIUS_BINS && a.radius64 != nullptr);
+  if (bins64) {
+    rmin64 = a.radius_stats64[2 * n + 0];
+    rmax64 = a.radius_stats64[2 * n + 1];
+  } else if (a.pur_mode == HALO_PUR_RADIUS_BINS) {
     rmin = a.radius_stats[4 * n + 0];
     rmax = a.radius_stats[4 * n + 1];
   }
@@ -76,6 +91,7 @@ __global__ void __launch_bounds__(SC_THREADS) score_pass_a_kernel(const ScoreArg
       const size_t g = plane + (size_t)y * a.W + x;
       if (a.unc_mode != HALO_UNC_ZERO) u = a.pixunc[g];
       if (a.pur_mode == HALO_PUR_LABEL_HIST) lab = a.label[g];
+      else if (bins64) lab = radius_bin64(a.radius64[g], rmin64, rmax64, a.n_bins);
       else if (a.pur_mode == HALO_PUR_RADIUS_BINS) lab = radius_bin(a.radius[g], rmin, rmax, a.n_bins);
       if (hist && lab < 255) atomicOr(&s_present[lab >> 5], 1u << (lab & 31));
     }
@@ -301,8 +317,8 @@ using namespace halo;
 
 extern "C" size_t halo_score_workspace_bytes(int N) { return N > 0 ? (size_t)N * 4 * sizeof(unsigned) : 0; }
 
-extern "C" int halo_score(const float* pixunc, const float* radius, const float* radius_stats, const uint8_t* label,
-                          const uint8_t* active, int unc_mode, int pur_mode, int normalize, int k, int pk, int n_bins,
+extern "C" int halo_score(const float* pixunc, const float* radius, const float* radius_stats, const double* radius64,
+                          const double* radius_stats64, const uint8_t* label, const uint8_t* active, int unc_mode, int pur_mode, int normalize, int k, int pk, int n_bins,
                           float* score, float* impurity, float* uncertainty, int N, int H, int W, void* ws,
                           size_t ws_bytes, halo_stream_t stream) {
   HALO_CHECK_ARG(score && uncertainty, "halo_score: score and uncertainty planes are required");
@@ -310,8 +326,10 @@ extern "C" int halo_score(const float* pixunc, const float* radius, const float*
   HALO_CHECK_ARG(unc_mode >= 0 && unc_mode <= 2 && pur_mode >= 0 && pur_mode <= 3, "halo_score: bad mode");
   HALO_CHECK_ARG(k > 0 && (k & 1) && pk > 0 && (pk & 1), "halo_score: window sizes must be odd (got k=%d pk=%d)", k, pk);
   HALO_CHECK_ARG(unc_mode == HALO_UNC_ZERO || pixunc, "halo_score: pixunc plane required");
-  HALO_CHECK_ARG((pur_mode != HALO_PUR_NORM && pur_mode != HALO_PUR_RADIUS_BINS) || radius, "halo_score: radius plane required");
-  HALO_CHECK_ARG(pur_mode != HALO_PUR_RADIUS_BINS || radius_stats, "halo_score: radius_stats required for radius bins");
+  HALO_CHECK_ARG(pur_mode != HALO_PUR_NORM || radius, "halo_score: radius plane required");
+  HALO_CHECK_ARG(pur_mode != HALO_PUR_RADIUS_BINS || (radius && radius_stats) || (radius64 && radius_stats64),
+                 "halo_score: radius bins need a radius plane with its stats (fp32 or fp64)");
+  HALO_CHECK_ARG((radius64 == nullptr) == (radius_stats64 == nullptr), "halo_score: radius64 and radius_stats64 go together");
   HALO_CHECK_ARG(pur_mode != HALO_PUR_LABEL_HIST || label, "halo_score: label plane required");
   HALO_CHECK_ARG(!(pur_mode == HALO_PUR_LABEL_HIST || pur_mode == HALO_PUR_RADIUS_BINS) || (n_bins >= 2 && n_bins <= 255),
                  "halo_score: n_bins must be in [2,255] (got %d)", n_bins);
@@ -328,6 +346,7 @@ extern "C" int halo_score(const float* pixunc, const float* radius, const float*
   cudaStream_t st = (cudaStream_t)stream;
   ScoreArgs a;
   a.pixunc = pixunc; a.radius = radius; a.radius_stats = radius_stats; a.label = label; a.active = active;
+  a.radius64 = radius64; a.radius_stats64 = radius_stats64;
   a.score = score; a.impurity = impurity; a.uncertainty = uncertainty; a.mm = (unsigned*)ws;
   a.unc_mode = unc_mode; a.pur_mode = pur_mode; a.normalize = normalize; a.k = k; a.pk = pk; a.n_bins = n_bins;
   a.N = N; a.H = H; a.W = W;

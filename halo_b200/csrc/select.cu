@@ -22,7 +22,7 @@ constexpr int SEL_TEAM_WARPS = 4;  // warps that walk the sorted candidate list 
 constexpr int SEL_BITS = 11;
 constexpr int SEL_BINS = 1 << SEL_BITS;
 constexpr size_t SEL_LIST_BYTES = 64 * 1024;  // candidate list: 8 192 fp32-score keys (4 096 fp64-score keys); power of two (bitonic)
-constexpr size_t SEL_SMEM_MAX = 220 * 1024;
+constexpr size_t SEL_SMEM_MAX = 212 * 1024;  // dynamic part: 227 KB opt-in limit minus the static SelShared (~9.1 KB) and slack
 
 template <typename S>
 struct SelTraits;

@@ -70,6 +70,8 @@ struct UpArgs {
   uint8_t* label;
   float* radius;
   float* stats;
+  double* radius64;              // optional fp64 copy of the radius plane + per-image {min,max} ("hyper" bins)
+  unsigned long long* stats64;
   int emb_kind, pixunc_mode, label_mode, norm_mode;
   int N, O, C, lh, lw, eh, ew, H, W;  // logits at lh x lw, embedding at eh x ew, outputs at H x W
   float c, inv_log19;
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(256) upsample_inputs_kernel(const UpArgs a) {
   const int X = blockIdx.x * blockDim.x + threadIdx.x;
   const int Y = blockIdx.y;
   float rmin = __int_as_float(0x7f800000), rmax = 0.f;
+  unsigned long long lo64 = 0x7ff0000000000000ull, hi64 = 0ull;
   if (X < a.W) {
     // torch area_pixel_compute_scale / source_index with align_corners=True, float opmath
     const size_t pix = ((size_t)n * a.H + Y) * a.W + X;
@@ -169,16 +172,21 @@ __global__ void __launch_bounds__(256) upsample_inputs_kernel(const UpArgs a) {
       n2 += 2.0 * (w00 * w01 * GR[j00] + w10 * w11 * GR[j10] + w00 * w10 * GD[j00] + w01 * w11 * GD[j01] +
                    w00 * w11 * GQ[j00] + w01 * w10 * GA[j00]);
       n2 = fmax(n2, 0.0);
-      float r;
+      double r64;
       if (a.norm_mode == HALO_NORM_EUCLID) {
-        r = (float)sqrt(n2);
+        r64 = sqrt(n2);
       } else {
         const double s = sqrt((double)a.c);
         const double t = fmin(s * sqrt(n2), 1.0 - 1e-7);  // geoopt artanh clamp (hyperbolic.py:83)
-        r = (float)((log1p(t) - log1p(-t)) / s);
+        r64 = (log1p(t) - log1p(-t)) / s;
       }
+      const float r = (float)r64;
       a.radius[pix] = r;
       rmin = rmax = r;
+      if (a.radius64 != nullptr) {
+        a.radius64[pix] = r64;
+        lo64 = hi64 = (unsigned long long)__double_as_longlong(r64);
+      }
     }
   }
   if (a.stats != nullptr && a.radius != nullptr) {
@@ -189,14 +197,31 @@ __global__ void __launch_bounds__(256) upsample_inputs_kernel(const UpArgs a) {
       atomicMax(reinterpret_cast<int*>(a.stats + 4 * n + 1), __float_as_int(rmax));
     }
   }
+  if (a.stats64 != nullptr && a.radius64 != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long l2 = __shfl_xor_sync(0xffffffffu, lo64, o), h2 = __shfl_xor_sync(0xffffffffu, hi64, o);
+      lo64 = l2 < lo64 ? l2 : lo64;
+      hi64 = h2 > hi64 ? h2 : hi64;
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(a.stats64 + 2 * n + 0, lo64);
+      atomicMax(a.stats64 + 2 * n + 1, hi64);
+    }
+  }
 }
 
-__global__ void up_stats_init_kernel(float* stats, int N) {
+__global__ void up_stats_init_kernel(float* stats, unsigned long long* stats64, int N) {
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
-    stats[4 * n + 0] = __int_as_float(0x7f800000);
-    stats[4 * n + 1] = 0.f;
-    stats[4 * n + 2] = 0.f;
-    stats[4 * n + 3] = 0.f;
+    if (stats != nullptr) {
+      stats[4 * n + 0] = __int_as_float(0x7f800000);
+      stats[4 * n + 1] = 0.f;
+      stats[4 * n + 2] = 0.f;
+      stats[4 * n + 3] = 0.f;
+    }
+    if (stats64 != nullptr) {
+      stats64[2 * n + 0] = 0x7ff0000000000000ull;
+      stats64[2 * n + 1] = 0ull;
+    }
   }
 }
 
@@ -210,9 +235,11 @@ extern "C" size_t halo_upsample_workspace_bytes(int N, int h, int w) {
 
 extern "C" int halo_upsample_score_inputs(const float* logits_lr, const void* emb_lr, int emb_kind, float c,
                                           const uint8_t* gt, int pixunc_mode, int label_mode, int norm_mode,
-                                          float* pixunc, uint8_t* label, float* radius, float* stats, int N, int O, int C,
-                                          int lh, int lw, int eh, int ew, int H, int W, void* ws, size_t ws_bytes,
-                                          halo_stream_t stream) {
+                                          float* pixunc, uint8_t* label, float* radius, float* stats, double* radius64,
+                                          double* stats64, int N, int O, int C, int lh, int lw, int eh, int ew, int H, int W,
+                                          void* ws, size_t ws_bytes, halo_stream_t stream) {
+  HALO_CHECK_ARG((radius64 == nullptr) == (stats64 == nullptr), "halo_upsample_score_inputs: radius64 and stats64 go together");
+  HALO_CHECK_ARG(!radius64 || (emb_lr && radius), "halo_upsample_score_inputs: radius64 needs the embedding and the fp32 radius plane");
   HALO_CHECK_ARG(N > 0 && H > 0 && W > 0, "halo_upsample_score_inputs: bad dims");
   HALO_CHECK_ARG(!logits_lr || (lh > 0 && lw > 0), "halo_upsample_score_inputs: bad logits size");
   HALO_CHECK_ARG(!emb_lr || (eh > 0 && ew > 0), "halo_upsample_score_inputs: bad embedding size");
@@ -226,7 +253,7 @@ extern "C" int halo_upsample_score_inputs(const float* logits_lr, const void* em
   cudaStream_t st = (cudaStream_t)stream;
   UpArgs a;
   a.logits = logits_lr; a.emb = emb_lr; a.gram = nullptr; a.gt = gt; a.pixunc = pixunc; a.label = label; a.radius = radius;
-  a.stats = stats; a.emb_kind = emb_kind; a.pixunc_mode = pixunc_mode; a.label_mode = label_mode; a.norm_mode = norm_mode;
+  a.stats = stats; a.radius64 = radius64; a.stats64 = reinterpret_cast<unsigned long long*>(stats64); a.emb_kind = emb_kind; a.pixunc_mode = pixunc_mode; a.label_mode = label_mode; a.norm_mode = norm_mode;
   a.N = N; a.O = O; a.C = C; a.lh = lh; a.lw = lw; a.eh = eh; a.ew = ew; a.H = H; a.W = W; a.c = c; a.inv_log19 = (float)(1.0 / log(19.0));
   if (emb_lr) {
     const size_t need = halo_upsample_workspace_bytes(N, eh, ew);
@@ -246,8 +273,8 @@ extern "C" int halo_upsample_score_inputs(const float* logits_lr, const void* em
     if (rc) return rc;
     a.gram = (const double*)ws;
   }
-  if (stats) {
-    up_stats_init_kernel<<<(N + 255) / 256, 256, 0, st>>>(stats, N);
+  if (stats || stats64) {
+    up_stats_init_kernel<<<(N + 255) / 256, 256, 0, st>>>(stats, a.stats64, N);
     int rc = launch_status("up_stats_init_kernel");
     if (rc) return rc;
   }

@@ -29,11 +29,31 @@ def _reference_cfg(path, default):
         return default
 
 
+def radius_f64(feat, c, kind):
+    """(N,H,W) fp64 radius plane + (N,2) fp64 {min,max}: the reference's own precision for the "hyper" bins
+    (floating_region.py:94-110) -- `halo_radius_f64`.  kind: "tangent" (raw fp32 features) or "ball" (fp32/fp64 points)."""
+    lib = nat.load()
+    nat.require_cuda(feat, "decoder_out")
+    if kind == "tangent":
+        feat, fk = feat.detach().float().contiguous(), nat.FEAT_TANGENT_F32
+    elif feat.dtype == torch.float64:
+        feat, fk = feat.detach().contiguous(), nat.FEAT_BALL_F64
+    else:
+        feat, fk = feat.detach().float().contiguous(), nat.FEAT_BALL_F32
+    N, C, H, W = feat.shape
+    r64 = torch.empty((N, H, W), dtype=torch.float64, device=feat.device)
+    st64 = torch.empty((N, 2), dtype=torch.float64, device=feat.device)
+    with torch.cuda.device(feat.device):
+        rc = lib.halo_radius_f64(nat.ptr(feat), fk, float(c), nat.ptr(r64), nat.ptr(st64), N, C, H, W, nat.stream_of(feat))
+    nat.check(rc, "halo_radius_f64")
+    return r64, st64
+
+
 def score_planes(pixunc, radius, radius_stats, label, active, *, unc_mode, pur_mode, normalize, k, pk, n_bins,
-                 want_impurity=True, want_maps=True):
+                 want_impurity=True, want_maps=True, radius64=None, radius_stats64=None):
     """Batched `halo_score` on device planes (N,H,W).  Returns (score, impurity|None, uncertainty)."""
     lib = nat.load()
-    ref = pixunc if pixunc is not None else radius
+    ref = pixunc if pixunc is not None else (radius if radius is not None else radius64)
     if ref is None:
         raise ValueError("score_planes: need at least one input plane")
     N, H, W = ref.shape
@@ -44,7 +64,8 @@ def score_planes(pixunc, radius, radius_stats, label, active, *, unc_mode, pur_m
     imp = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need_imp else None
     ws = nat.workspace.get(dev, "score", lib.halo_score_workspace_bytes(N))
     with torch.cuda.device(dev):
-        rc = lib.halo_score(nat.ptr(pixunc), nat.ptr(radius), nat.ptr(radius_stats), nat.ptr(label), nat.ptr(active),
+        rc = lib.halo_score(nat.ptr(pixunc), nat.ptr(radius), nat.ptr(radius_stats), nat.ptr(radius64),
+                            nat.ptr(radius_stats64), nat.ptr(label), nat.ptr(active),
                             unc_mode, pur_mode, (1 if want_maps else 2) if normalize else 0, k, pk, n_bins, nat.ptr(score), nat.ptr(imp),
                             nat.ptr(unc), N, H, W, nat.ptr(ws), ws.numel(), nat.stream_of(ref))
     nat.check(rc, "halo_score")
@@ -152,17 +173,22 @@ class FloatingRegionScore(nn.Module):
                                            nat.LABEL_GT_FILLED if label_mode == "gt_filled" else nat.LABEL_ARGMAX,
                                            nat.ptr(pixunc), nat.ptr(label), N, O, H, W, nat.stream_of(logit))
             nat.check(rc, "halo_logits_stats")
-        radius = stats = None
-        if pur_mode in (nat.PUR_NORM, nat.PUR_RADIUS_BINS):
-            if decoder_out is None:
-                raise ValueError("decoder_out is required by pur_type '%s'" % pur_type)
-            radius, stats = self._radius_plane(decoder_out, norm_mode, pur_mode == nat.PUR_RADIUS_BINS)
+        radius = stats = r64 = st64 = None
+        if pur_mode in (nat.PUR_NORM, nat.PUR_RADIUS_BINS) and decoder_out is None:
+            raise ValueError("decoder_out is required by pur_type '%s'" % pur_type)
+        if pur_mode == nat.PUR_NORM:
+            radius, stats = self._radius_plane(decoder_out, norm_mode, False)
+        elif pur_mode == nat.PUR_RADIUS_BINS:   # bins follow the reference's fp64 arithmetic (:94-110)
+            if isinstance(decoder_out, PoincareEmbedding):
+                r64, st64 = radius_f64(decoder_out.u, self.mapper.c, "tangent")
+            else:
+                r64, st64 = radius_f64(decoder_out, self.mapper.c, "ball")
         n_bins = self.K if pur_mode == nat.PUR_RADIUS_BINS else self.in_channels
-        if pixunc is None and radius is None:  # "none"/"none": the kernel still needs a shape carrier
+        if pixunc is None and radius is None and r64 is None:  # "none"/"none": the kernel still needs a shape carrier
             pixunc = torch.zeros((N, H, W), dtype=torch.float32, device=dev)
         score, imp, unc = score_planes(pixunc, radius, stats, label, None, unc_mode=unc_mode, pur_mode=pur_mode,
                                        normalize=normalize, k=self.size, pk=self.purity_size, n_bins=n_bins,
-                                       want_impurity=True)
+                                       want_impurity=True, radius64=r64, radius_stats64=st64)
         if N == 1:
             return score[0], imp[0], unc[0]
         return score, imp, unc
@@ -199,7 +225,10 @@ class FloatingRegionScore(nn.Module):
         pixunc = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need_pixunc else None
         label = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if need_label else None
         radius = torch.empty((N, H, W), dtype=torch.float32, device=dev) if need_radius else None
-        stats = torch.empty((N, 4), dtype=torch.float32, device=dev) if pur_mode == nat.PUR_RADIUS_BINS else None
+        stats = r64 = st64 = None
+        if pur_mode == nat.PUR_RADIUS_BINS:   # bins follow the reference's fp64 arithmetic (:94-110)
+            r64 = torch.empty((N, H, W), dtype=torch.float64, device=dev)
+            st64 = torch.empty((N, 2), dtype=torch.float64, device=dev)
         emb, emb_kind, C = None, nat.FEAT_BALL_F32, 0
         if need_radius:
             if decoder_out_lr is None:
@@ -224,15 +253,15 @@ class FloatingRegionScore(nn.Module):
                 nat.ptr(gt8), nat.PIXUNC_ONE_MINUS_PGT if pixunc_mode == "one_minus_pgt" else nat.PIXUNC_ENTROPY,
                 nat.LABEL_GT_FILLED if label_mode == "gt_filled" else nat.LABEL_ARGMAX,
                 nat.NORM_EUCLID if norm_mode == "euclid" else nat.NORM_RADIUS, nat.ptr(pixunc), nat.ptr(label),
-                nat.ptr(radius), nat.ptr(stats), N, O, C, h, w, eh, ew, H, W, nat.ptr(ws), ws.numel(),
-                nat.stream_of(logit_lr))
+                nat.ptr(radius), nat.ptr(stats), nat.ptr(r64), nat.ptr(st64), N, O, C, h, w, eh, ew, H, W, nat.ptr(ws),
+                ws.numel(), nat.stream_of(logit_lr))
         nat.check(rc, "halo_upsample_score_inputs")
         n_bins = self.K if pur_mode == nat.PUR_RADIUS_BINS else self.in_channels
         if pixunc is None and radius is None:
             pixunc = torch.zeros((N, H, W), dtype=torch.float32, device=dev)
         score, imp, unc = score_planes(pixunc, radius, stats, label, None, unc_mode=unc_mode, pur_mode=pur_mode,
                                        normalize=normalize, k=self.size, pk=self.purity_size, n_bins=n_bins,
-                                       want_impurity=True)
+                                       want_impurity=True, radius64=r64, radius_stats64=st64)
         if N == 1:
             return score[0], imp[0], unc[0]
         return score, imp, unc

@@ -247,6 +247,17 @@ class PoincareEmbedding(object):
         return func(*conv(args), **{k: conv(v) for k, v in kwargs.items()})
 
 
+def _logmap0(x, c):
+    """u with expmap0(u) == x for (N,C,H,W) points on the ball, in torch ops (differentiable w.r.t. x):
+    u = artanh(sqrt(c)|x|) x / (sqrt(c)|x|)   (geoopt logmap0, k<0 branch; hyperbolic.py:60 is its only caller in the
+    reference).  Computed in float64 and returned in float32 (what the fused head reads)."""
+    xd = x.double()
+    s = math.sqrt(float(c))
+    n = xd.norm(dim=1, keepdim=True).clamp_min(1e-15)
+    t = (s * n).clamp(max=1.0 - 1e-7)
+    return (torch.atanh(t) / (s * n) * xd).float()
+
+
 def _norm_from_tangent(u, c, norm_mode):
     """radius / |x| plane + per-image min/max from RAW features: r = min(2|u|, 2 artanh(1-1e-5)/sqrt(c))."""
     lib = nat.load()
@@ -302,6 +313,10 @@ class HyperMapper(object):
         d = dim if dim >= 0 else x.dim() + dim
         if x.dim() == 4 and d == 1:
             return PoincareEmbedding(x if x.dtype == torch.float32 else x.float(), self.c)
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise NotImplementedError(
+                "HyperMapper.expmap: the eager path (anything but (N,C,H,W) features with dim=1) is forward-only; "
+                "detach the input or use the (N,C,H,W) layout, whose fused head is differentiable")
         lib = nat.load()
         xm = x.detach().float().movedim(d, 0)
         rest = xm.shape[1:]
@@ -351,10 +366,13 @@ class HyperMLR(nn.Module):
                                want_radius=True, want_stats=True)
             inputs._radius, inputs._radius_stats = res["radius"], res["stats"]
             return res["logits"]
-        if torch.is_grad_enabled() and inputs.requires_grad:
-            raise NotImplementedError(
-                "HyperMLR: gradients w.r.t. points already on the ball are not implemented; "
-                "pass the PoincareEmbedding returned by HyperMapper.expmap (fused, differentiable)")
+        if torch.is_grad_enabled() and (inputs.requires_grad or self.P_MLR.requires_grad or self.A_MLR.requires_grad):
+            # Differentiable route for points ALREADY on the ball (the reference's HyperMLR is differentiable w.r.t. x, P
+            # and A on this path too): pull the points back to the tangent space with torch ops (logmap0, differentiable,
+            # fp64 like the reference's embedding) and run the fused forward / backward on the result -- for points inside
+            # the projection radius expmap0(logmap0(x)) == x, so logits and all three gradients are the reference's.
+            nat.require_cuda(inputs, "inputs")
+            return _FusedHead.apply(_logmap0(inputs, self.c), self.P_MLR, self.A_MLR, float(self.c), None)
         return head_forward(inputs, self.P_MLR, self.A_MLR, self.c, kind="ball", want_logits=True)["logits"]
 
     def forward(self, x):

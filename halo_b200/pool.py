@@ -14,7 +14,7 @@ import torch
 
 from . import _native as nat
 from .active import select_planes
-from .floating_region import modes_for, score_planes
+from .floating_region import modes_for, radius_f64, score_planes
 from .hyperbolic import head_forward
 
 
@@ -53,20 +53,25 @@ def acquire_batch(feat, P, A, cfg, gt, active, selected, active_mask, *, want_sc
     unc_mode, pixunc_mode, pur_mode, label_mode, norm_mode = modes_for(cfg.uncertainty, cfg.purity)
     need_pixunc = unc_mode != nat.UNC_ZERO
     need_label = pur_mode == nat.PUR_LABEL_HIST
-    need_radius = pur_mode in (nat.PUR_NORM, nat.PUR_RADIUS_BINS)
+    need_radius = pur_mode == nat.PUR_NORM
     need_gt = pixunc_mode == "one_minus_pgt" or label_mode == "gt_filled"
     res = head_forward(feat, P, A, cfg.curvature, kind="tangent", want_logits=False, want_radius=need_radius,
-                       want_pixunc=need_pixunc, want_label=need_label, want_stats=pur_mode == nat.PUR_RADIUS_BINS,
+                       want_pixunc=need_pixunc, want_label=need_label, want_stats=False,
                        gt=gt if need_gt else None, pixunc_mode=pixunc_mode, label_mode=label_mode, norm_mode=norm_mode)
+    r64 = st64 = None
+    if pur_mode == nat.PUR_RADIUS_BINS:
+        # "hyper": the K radius bins follow the reference's fp64 arithmetic (floating_region.py:94-110), which costs a
+        # second pass over the features (fp64 |u|^2); the other purities stay on the single fused pass
+        r64, st64 = radius_f64(feat, cfg.curvature, "tangent")
     pixunc = res["pixunc"]
-    if pixunc is None and res["radius"] is None:
+    if pixunc is None and res["radius"] is None and r64 is None:
         pixunc = torch.zeros((B, H, W), dtype=torch.float32, device=feat.device)
     k = 2 * cfg.radius_k + 1
     pk = 3 if cfg.purity == "hyper" else k
     n_bins = cfg.K if pur_mode == nat.PUR_RADIUS_BINS else cfg.num_classes
-    score, _, _ = score_planes(pixunc, res["radius"], res["stats"], res["label"], active, unc_mode=unc_mode,
+    score, _, _ = score_planes(pixunc, res["radius"], None, res["label"], active, unc_mode=unc_mode,
                                pur_mode=pur_mode, normalize=cfg.normalize, k=k, pk=pk, n_bins=n_bins,
-                               want_impurity=False, want_maps=False)
+                               want_impurity=False, want_maps=False, radius64=r64, radius_stats64=st64)
     out = {}
     if want_score:
         out["score"] = score.clone()

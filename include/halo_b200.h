@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define HALO_ABI_VERSION 1
+#define HALO_ABI_VERSION 2
 
 typedef void* halo_stream_t; /* cudaStream_t / CUstream of the caller; NULL = legacy default stream */
 
@@ -79,6 +79,18 @@ typedef enum {
 
 int halo_abi_version(void);
 const char* halo_last_error(void);
+const char* halo_source_hash(void); /* "HALO_SRC_SHA256=<hex>": content hash of the sources the library was built from */
+
+/* Which kernel variants the LAST halo_head_fwd / halo_head_bwd call on this thread launched (OR of the bits below).
+ * Shapes outside the tensor-core envelope (see each entry point) run fp32 CUDA-core kernels that are several times
+ * slower; the library also prints one line on stderr the first time that happens (HALO_QUIET=1 silences it). */
+#define HALO_PATH_FWD_TC 0x01       /* head_fwd_tc_kernel: tcgen05 3xTF32, TMA */
+#define HALO_PATH_FWD_CUDA_CORE 0x02
+#define HALO_PATH_BWD_PIX_TC 0x04   /* head_bwd_tc_kernel */
+#define HALO_PATH_BWD_PIX_CUDA_CORE 0x08
+#define HALO_PATH_BWD_DW_TC 0x10    /* head_bwd_dw_tc_kernel */
+#define HALO_PATH_BWD_DW_CUDA_CORE 0x20
+int halo_last_path(void);
 
 /* ---- Poincare-ball classifier head, forward -------------------------------------------------------
  * Replaces HyperMapper.expmap (core/utils/hyperbolic.py:28-39), HyperMLR.forward/_hyper_logits
@@ -114,6 +126,13 @@ int halo_expmap0_project(const float* u, void* x_out, int out_f64, float c, int 
 /* halo_ball_norm: poincare_distance_origin (:74-83) or ||x|| of points on the ball; stats as above (or NULL) */
 int halo_ball_norm(const void* x, int x_f64, float c, int norm_mode, float* out, float* stats,
                    int N, int C, int H, int W, halo_stream_t stream);
+/* halo_radius_f64: the radius plane in the reference's own precision, for the "hyper" purity
+ * (core/active/floating_region.py:94-110 quantises an fp64 poincare_distance_origin, hyperbolic.py:74-83, into K bins with
+ * round-half-even; an fp32 radius lands ~1e-4 of the pixels in the neighbouring bin).  feat per halo_feat_kind: raw fp32
+ * features (closed form of expmap0 + project + dist0 from an fp64 |u|^2) or ball points fp32/fp64.
+ *   radius64 [N,H,W] f64;  stats64 [N,2] f64 = {min,max} of each image's plane. */
+int halo_radius_f64(const void* feat, int feat_kind, float c, double* radius64, double* stats64,
+                    int N, int C, int H, int W, halo_stream_t stream);
 /* halo_logits_stats: softmax -> per-pixel uncertainty + label from explicit logits
  * (floating_region.py:151-152, 70-83, 123-127, 166, 172-173). */
 int halo_logits_stats(const float* logits, const uint8_t* gt, int pixunc_mode, int label_mode,
@@ -126,25 +145,30 @@ int halo_logits_stats(const float* logits, const uint8_t* gt, int pixunc_mode, i
  *   logits_lr [N,O,lh,lw] f32 | NULL;  emb_lr [N,C,eh,ew] per emb_kind (halo_feat_kind: raw features get
  *   expmap0+project at the low-resolution pixels first) | NULL -- the two may come at different resolutions (the
  *   DeepLab v3+ head up-samples only its logits, classifier.py:556-557);  outputs at [N,H,W]: pixunc f32, label u8,
- *   radius f32, stats [N,4].  ws: halo_upsample_workspace_bytes(N,eh,ew), required whenever emb_lr is given (it holds the
+ *   radius f32, stats [N,4]; radius64 [N,H,W] f64 + stats64 [N,2] f64 (both or neither; the fp64 radius of the interpolated
+ *   embedding and its per-image extrema, as halo_radius_f64, for the "hyper" purity).  ws: halo_upsample_workspace_bytes(N,eh,ew), required whenever emb_lr is given (it holds the
  *   per-low-resolution-pixel Gram entries and exp-map factors the output pixels evaluate the norm from). */
 size_t halo_upsample_workspace_bytes(int N, int h, int w);
 int halo_upsample_score_inputs(const float* logits_lr, const void* emb_lr, int emb_kind, float c, const uint8_t* gt,
                                int pixunc_mode, int label_mode, int norm_mode, float* pixunc, uint8_t* label,
-                               float* radius, float* stats, int N, int O, int C, int lh, int lw, int eh, int ew,
+                               float* radius, float* stats, double* radius64, double* stats64,
+                               int N, int O, int C, int lh, int lw, int eh, int ew,
                                int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
 
 /* ---- floating-region score (core/active/floating_region.py:129-217 after the softmax) ---------------
  *   pixunc [N,H,W] f32, radius [N,H,W] f32 (+ its stats [N,4]), label [N,H,W] u8, active [N,H,W] u8|NULL
  *   k = uncertainty window (odd), pk = purity window (odd; 3 when the module was built for "hyper"),
  *   n_bins = class count for LABEL_HIST or K for RADIUS_BINS.
+ *   radius64 [N,H,W] f64 + radius_stats64 [N,2] f64 (both or neither, from halo_radius_f64 / halo_upsample_score_inputs):
+ *   when given, HALO_PUR_RADIUS_BINS quantises THEM, in fp64 like the reference (floating_region.py:94-110), and the fp32
+ *   radius / radius_stats may be NULL in that mode.
  *   normalize: 0 = off; 1 = min-max normalise both maps (floating_region.py:206-208) and return them normalised;
  *              2 = same score, but the impurity/uncertainty planes are left un-normalised (scratch only).
  *   score [N,H,W] f32 (active!=0 -> -inf, build.py:146); impurity / uncertainty [N,H,W] f32 are
  *   REQUIRED scratch+outputs (they receive the maps the reference returns). */
 size_t halo_score_workspace_bytes(int N);
-int halo_score(const float* pixunc, const float* radius, const float* radius_stats, const uint8_t* label,
-               const uint8_t* active, int unc_mode, int pur_mode, int normalize, int k, int pk, int n_bins,
+int halo_score(const float* pixunc, const float* radius, const float* radius_stats,
+               const double* radius64, const double* radius_stats64, const uint8_t* label, const uint8_t* active, int unc_mode, int pur_mode, int normalize, int k, int pk, int n_bins,
                float* score, float* impurity, float* uncertainty, int N, int H, int W,
                void* ws, size_t ws_bytes, halo_stream_t stream);
 

@@ -25,7 +25,17 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), "libhalo_sm100.so does not export %s" % s
     assert set(syms) == set(nat.EXPORTED_SYMBOLS), "python binding and header disagree"
-    assert lib.halo_abi_version() == 1
+    assert lib.halo_abi_version() == nat.ABI_VERSION == 2
+
+
+def test_library_carries_the_hash_of_its_sources():
+    """A stale library (sources edited, .so not rebuilt) is detected by content, not by mtime."""
+    from halo_b200 import _build
+
+    lib = nat.load()
+    assert lib.halo_source_hash().decode() == "HALO_SRC_SHA256=" + _build.source_hash()
+    assert _build.built_hash() == _build.source_hash() and not _build.stale()
+    assert lib.halo_last_path() == 0 or lib.halo_last_path() > 0   # exported, callable without a GPU
 
 
 def test_workspace_queries_are_pure():
@@ -50,14 +60,18 @@ def test_bad_arguments_return_status_not_crash():
     assert rc == nat.ERR_UNSUPPORTED
     rc = lib.halo_head_fwd(one, 0, one, one, 1.0, None, None, None, None, None, None, 0, 0, 0, 1, 8, 19, 4, 4, one, 8, None)
     assert rc == nat.ERR_WORKSPACE
-    rc = lib.halo_score(one, one, None, None, None, 0, 0, 1, 4, 3, 19, one, None, one, 1, 8, 8, one, 64, None)
+    rc = lib.halo_score(one, one, None, None, None, None, None, 0, 0, 1, 4, 3, 19, one, None, one, 1, 8, 8, one, 64, None)
     assert rc == nat.ERR_BAD_ARG and "odd" in nat.last_error()
     rc = lib.halo_round_delta_pack(None, one, one, one, 1, 4, 8, 8, 1, None)
     assert rc == nat.ERR_BAD_ARG and "halo_round_delta_pack" in nat.last_error()
     rc = lib.halo_round_delta_apply(one, one, one, one, one, 1, 0, 8, 8, 1, None)
     assert rc == nat.ERR_BAD_ARG and "halo_round_delta_apply" in nat.last_error()
-    rc = lib.halo_upsample_score_inputs(None, one, 0, 1.0, None, 0, 0, 0, None, None, one, None, 1, 0, 8, 0, 0, 4, 4, 8, 8, None, 0, None)
+    rc = lib.halo_upsample_score_inputs(None, one, 0, 1.0, None, 0, 0, 0, None, None, one, None, None, None, 1, 0, 8, 0, 0, 4, 4, 8, 8, None, 0, None)
     assert rc == nat.ERR_WORKSPACE   # an embedding always needs the Gram workspace
+    rc = lib.halo_score(one, None, None, one, None, None, None, 0, 2, 1, 3, 3, 100, one, one, one, 1, 8, 8, one, 64, None)
+    assert rc == nat.ERR_BAD_ARG and "radius" in nat.last_error()   # fp64 radius plane without its extrema
+    rc = lib.halo_radius_f64(one, 7, 1.0, one, one, 1, 8, 4, 4, None)
+    assert rc == nat.ERR_BAD_ARG and "feat_kind" in nat.last_error()
     rc = lib.halo_select_f32(one, one, one, one, one, -1, 1, 5, 0, one, None, 1, 8, 8, one, 1 << 20, None)
     assert rc == nat.ERR_BAD_ARG
     with pytest.raises(ValueError):

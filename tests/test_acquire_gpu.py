@@ -33,6 +33,9 @@ def oracle_round(feat, gt, P, A, cfg, active=None):
     ("ripu", halo_b200.AcquisitionConfig(budget=0.022, purity="ripu", normalize=False), (2, 64, 19, 96, 160)),
     ("synthia_5x5", halo_b200.AcquisitionConfig(num_classes=16, radius_k=2, budget=0.022), (2, 64, 16, 96, 160)),
     ("pixel_mode", halo_b200.AcquisitionConfig(radius_k=0, mask_radius_k=0, budget=0.01), (1, 64, 19, 96, 160)),
+    # the reference's default purity (defaults.py:68): K = 100 radius bins, 3x3 purity window, bins formed in fp64
+    ("hyper_default", halo_b200.AcquisitionConfig(budget=0.022, purity="hyper"), (2, 64, 19, 96, 160)),
+    ("hyper_c256", halo_b200.AcquisitionConfig(budget=0.022, purity="hyper", normalize=False, K=50), (1, 256, 19, 128, 256)),
 ])
 def test_acquire_batch_matches_oracle(name, cfg, shape):
     n, C, O, H, W = shape

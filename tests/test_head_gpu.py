@@ -252,3 +252,50 @@ def test_tiny_planes_forward_and_backward(shape):
     assert rel_err(halo_b200.head_forward(*args, want_logits=True)["logits"], logits_ref) <= TOL
     du, dP, dA = halo_b200.head_backward(*args, dl.to(DEV))
     assert rel_err(du, du_ref) <= 1e-4 and rel_err(dP, dP_ref) <= 1e-4 and rel_err(dA, dA_ref) <= 1e-4
+
+
+def test_autograd_from_points_already_on_the_ball():
+    """HyperMLR fed a plain tensor of ball points (not the lazy handle) stays differentiable w.r.t. x, P and A like the
+    reference's module (hyperbolic.py:120-188): frozen-backbone / precomputed-embedding callers get gradients, not a
+    silent None (ADVICE r1)."""
+    C, O, H, W = 64, 19, 10, 12
+    P, A = synth.head_params(O, C, seed=21, dtype=torch.float64)
+    x = ohead.expmap(torch.randn(2, C, H, W) * 0.1, 1.0, dim=1)
+    target = torch.randint(0, O, (2, H, W))
+    x0, P0, A0 = x.clone().requires_grad_(True), P.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    torch.nn.functional.cross_entropy(ohead.mlr_logits(x0, P0, A0, 1.0).float(), target).backward()
+    mlr = halo_b200.HyperMLR(C, O, c=1.0).to(DEV)
+    mlr.load_state_dict({"P_MLR": P, "A_MLR": A})
+    for x_needs_grad in (True, False):          # detached embeddings must still give parameter gradients
+        mlr.zero_grad()
+        x1 = x.to(DEV).requires_grad_(x_needs_grad)
+        out = mlr(x1)
+        assert out.grad_fn is not None
+        torch.nn.functional.cross_entropy(out.float(), target.to(DEV)).backward()
+        assert rel_err(mlr.P_MLR.grad, P0.grad) <= 1e-4 and rel_err(mlr.A_MLR.grad, A0.grad) <= 1e-4
+        if x_needs_grad:
+            assert rel_err(x1.grad, x0.grad) <= 1e-4
+    with torch.no_grad():                        # forward-only: the ball kernel, same logits
+        assert rel_err(mlr(x.to(DEV)), ohead.mlr_logits(x, P, A, 1.0)) <= TOL
+    with pytest.raises(NotImplementedError):     # the eager (non NCHW) expmap is forward-only and says so
+        halo_b200.HyperMapper(1.0).expmap(torch.randn(5, 33, device=DEV, requires_grad=True), dim=-1)
+
+
+def test_last_path_reports_the_kernel_variant():
+    """halo_last_path(): shapes that fall off the tensor-core envelope are visible to the caller (VERDICT r1 weak #10)."""
+    from halo_b200 import _native as nat
+
+    P, A = synth.head_params(19, 64, seed=1, device=DEV)
+    u = torch.randn(1, 64, 16, 16, device=DEV) * 0.1
+    halo_b200.head_forward(u, P, A, 1.0)
+    assert nat.last_path() == ("fwd:tcgen05",)
+    halo_b200.head_forward(u, P, A, 1.0, tensor_cores=False)
+    assert nat.last_path() == ("fwd:cuda_core",)
+    P2, A2 = synth.head_params(19, 48, seed=1, device=DEV)          # C % 32 != 0: CUDA cores
+    halo_b200.head_forward(torch.randn(1, 48, 16, 16, device=DEV) * 0.1, P2, A2, 1.0)
+    assert nat.last_path() == ("fwd:cuda_core",)
+    dl = torch.randn(1, 19, 16, 16, device=DEV) * 1e-3
+    halo_b200.head_backward(u, P, A, 1.0, dl)
+    assert nat.last_path()[0] == "bwd_pix:tcgen05"
+    halo_b200.head_backward(torch.randn(1, 48, 16, 16, device=DEV) * 0.1, P2, A2, 1.0, dl)
+    assert nat.last_path() == ("bwd_pix:cuda_core", "bwd_dw:cuda_core")

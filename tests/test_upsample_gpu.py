@@ -26,6 +26,8 @@ DEV = "cuda"
     (32, 16, 17, 23, 17, 23, 50, 71, "entropy", "euc_norm", False),    # odd sizes
     (32, 19, 16, 24, 16, 24, 48, 72, "entropy", "ripu", False),
     (32, 19, 16, 24, 16, 24, 48, 72, "pixel_entropy", "radius", True),
+    (32, 19, 16, 24, 16, 24, 48, 72, "entropy", "hyper", True),        # K=100 radius bins in fp64 (floating_region.py:94-110)
+    (64, 19, 40, 80, 20, 40, 96, 160, "entropy", "hyper", False),
 ])
 @pytest.mark.parametrize("emb_kind", ["lazy", "ball64"])
 def test_upsampled_score_matches_reference_sequence(case, emb_kind):
