@@ -26,7 +26,7 @@ import torch  # noqa: E402
 WORKLOAD = dict(name="cfg2_gtav_cityscapes", pool_images=2975, H=640, W=1280, C=256, O=19, radius_k=1,
                 mask_radius_k=5, budget=0.05, n_rounds=1, uncertainty="entropy", purity="radius", normalize=True,
                 curvature=1.0, sigma=0.1)
-KERNELS_PER_STEP = 7  # head_pack, head_pack_tc, head_fwd_tc, score_init, score_pass_a, score_pass_b, select
+KERNELS_PER_STEP = 7  # head_pack, head_pack_tc, head_fwd_tc, score_init, score_pass_a, score_pass_b, select (+1 rows_pack)
 
 
 _JSON_FD = None
@@ -246,6 +246,108 @@ def workload_config(batch, note=None):
 # ------------------------------------------------------------------------------------------------------------
 # this repo's arm
 # ------------------------------------------------------------------------------------------------------------
+def traffic_from_profiles(batch):
+    """DRAM bytes per launch of K1 from the committed ncu --set full capture, scaled to `batch` images -- only while the
+    capture still describes the kernel: the json names the sha256 of csrc/head_fwd_tc.cu it was taken on."""
+    import hashlib
+
+    try:
+        with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+            t = json.load(f)
+        with open(os.path.join(ROOT, "halo_b200", "csrc", "head_fwd_tc.cu"), "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()
+        if t.get("kernel_source_sha256") != sha:
+            return None, "profiles/k1_traffic.json is stale (K1 source changed since the ncu capture)"
+        return float(t["dram_bytes_per_image"]) * batch, "profiles/k1_traffic.json (%s)" % t.get("source", "ncu")
+    except Exception as e:  # noqa: BLE001
+        return None, "unavailable (%s)" % type(e).__name__
+
+
+class PoolShard:
+    """This rank's shard of the 2 975-image pool, streamed through ONE resident batch of HBM (124 GB of features per 148
+    images: the pool itself is 2.5 TB).  `provider(lo, hi)` regenerates the features of pool images [lo, hi) in place,
+    per image from its own seed (so any sharding of the pool sees the same images), resets the state planes, and brackets
+    itself with CUDA events so that the generation stays OUT of the measured round time."""
+
+    def __init__(self, B, C, O, H, W, sigma, dev):
+        self.B, self.C, self.O, self.H, self.W, self.sigma, self.dev = B, C, O, H, W, sigma, dev
+        self.feat = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        self.gt = torch.empty((B, H, W), dtype=torch.uint8, device=dev)
+        self.active = torch.zeros((B, H, W), dtype=torch.uint8, device=dev)
+        self.selected = torch.zeros((B, H, W), dtype=torch.uint8, device=dev)
+        self.active_mask = torch.full((B, H, W), 255, dtype=torch.uint8, device=dev)
+        self.gen = torch.Generator(device=dev)
+        self.segments = []          # (start_event, end_event) of the timed stretches between two generations
+        self._open = None
+
+    def fill(self, lo, hi):
+        for k, i in enumerate(range(lo, hi)):
+            self.gen.manual_seed(1234 + i)
+            self.feat[k].normal_(0.0, self.sigma, generator=self.gen)
+            self.gt[k] = torch.randint(0, self.O, (self.H, self.W), generator=self.gen, device=self.dev, dtype=torch.int16).to(torch.uint8)
+            self.gt[k].masked_fill_(torch.rand((self.H, self.W), generator=self.gen, device=self.dev) < 0.05, 255)
+
+    def close_segment(self):
+        if self._open is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.segments.append((self._open, e))
+            self._open = None
+
+    def provider(self, lo, hi):
+        self.close_segment()
+        b = hi - lo
+        self.fill(lo, hi)
+        self.active[:b].zero_(); self.selected[:b].zero_(); self.active_mask[:b].fill_(255)
+        self._open = torch.cuda.Event(enable_timing=True)
+        self._open.record()
+        return dict(feat=self.feat[:b], gt=self.gt[:b], active=self.active[:b], selected=self.selected[:b],
+                    active_mask=self.active_mask[:b])
+
+    def timed_ms(self):
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in self.segments)
+
+
+def run_full_round(shard, P, A, cfg, world, distributed, dev):
+    """ONE real acquisition round over the whole 2 975-image pool (BASELINE.json configs[1] / [2]): every image generated
+    from its own seed, scored and selected on the rank that owns it, ONE packed all-gather at the end, every rank replays
+    all rows onto its replica of the pool's masks, and a 64-bit checksum of (masks, counts) is compared across ranks.
+    Timed = the K1/K2/K3/pack stretches of every batch + the exchange and replay (feature generation excluded), max over
+    ranks."""
+    import torch.distributed as dist
+
+    from halo_b200 import pool
+
+    w = WORKLOAD
+    n_images, H, W = w["pool_images"], w["H"], w["W"]
+    ex = pool.RoundExchange(n_images, H, W, cfg.regions_per_image(H, W), cfg.radius_k, dev)
+    masks = torch.full((n_images, H, W), 255, dtype=torch.uint8, device=dev)
+    shard.segments.clear()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    t0 = time.perf_counter()
+    out = pool.acquire_pool(shard.provider, n_images, P, A, cfg, batch_size=shard.B, exchange=ex, masks=masks, keep_local=False)
+    shard.close_segment()
+    ms = torch.tensor([shard.timed_ms()], dtype=torch.float64, device=dev)
+    wall = time.perf_counter() - t0
+    if distributed:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    checksum, agree = ex.verify(out["active_mask"], out["n_picked"])
+    lo, hi = out["range"]
+    cnt = out["n_picked"]
+    secs = float(ms.item()) / 1e3
+    return {"images": n_images, "images_this_rank": hi - lo, "batches_this_rank": len(shard.segments),
+            "seconds": round(secs, 4), "Mpixel/s": round(n_images * H * W / secs / 1e6, 1),
+            "wall_seconds_with_feature_generation": round(wall, 2), "exchanges": 1 if distributed else 0,
+            "exchange_bytes_per_rank": ex.bytes_per_rank() if distributed else 0,
+            "picks_min": int(cnt.min().item()), "picks_max": int(cnt.max().item()), "labelled_pixels": int((out["active_mask"] != 255).sum().item()),
+            "checksum": "%016x" % checksum, "replicas_agree": agree,
+            "note": "timed: K1+K2+K3+pack of every batch and the final all-gather + replay (CUDA events, max over ranks); "
+                    "per-image feature generation between batches is not timed (the pool, 2.5 TB, does not fit HBM)"}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -270,15 +372,18 @@ def run_ours(args):
     cfg = make_cfg()
     B, C, O, H, W = args.batch, w["C"], w["O"], w["H"], w["W"]
     P, A = synth.head_params(O, C, seed=0, device=dev)
-    # resident batch of this rank's shard of the pool (weak scaling: B images per GPU per step)
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    feat = torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
-    for i in range(B):
-        feat[i] = torch.randn((C, H, W), generator=g, device=dev, dtype=torch.float32) * w["sigma"]
-    gt = torch.randint(0, O, (B, H, W), generator=g, device=dev, dtype=torch.int64).to(torch.uint8)
-    gt[torch.rand((B, H, W), generator=g, device=dev) < 0.05] = 255
+    # this rank's shard of the pool, streamed through one resident batch (B images = 124 GB of features at B = 148)
+    n_images = w["pool_images"]
+    lo, hi = pool.shard_range(n_images, rank, world)
+    shard = PoolShard(B, C, O, H, W, w["sigma"], dev)
+    shard.fill(lo, min(lo + B, hi))
+    feat, gt = shard.feat, shard.gt
+    # the steps walk through consecutive rounds over the shard: batches of B images (the last one of a round is ragged),
+    # the round's ONE exchange after its last batch.  Features of the resident batch are reused by every step (the pool
+    # does not fit HBM); the mask state is fresh per step, allocated up front so that no fill runs inside the timed region.
+    sizes = [min(B, hi - b0) for b0 in range(lo, hi, B)]
+    R = len(sizes)
     total_steps = args.steps + args.warmup
-    # fresh round-1 state per step, allocated up front so that no fill kernel runs inside the timed region
     n_state = min(total_steps, 16)
     state = [dict(active=torch.zeros((B, H, W), dtype=torch.uint8, device=dev),
                   selected=torch.zeros((B, H, W), dtype=torch.uint8, device=dev),
@@ -287,22 +392,32 @@ def run_ours(args):
     def reset(s):
         s["active"].zero_(); s["selected"].zero_(); s["active_mask"].fill_(255)
 
-    # N > 1: every rank keeps a replica of the job's label masks; a step all-gathers the round's delta (pick counts, picks
-    # and the labels of their windows: 59 KB per image instead of the 819 KB plane) and replays it onto the replica
-    replica = torch.full((B * world, H, W), 255, dtype=torch.uint8, device=dev) if distributed else None
+    ex = pool.RoundExchange(n_images, H, W, cfg.regions_per_image(H, W), cfg.radius_k, dev)
+    replica = torch.full((n_images, H, W), 255, dtype=torch.uint8, device=dev)
+    counts = torch.zeros((n_images,), dtype=torch.int32, device=dev)
+    launches = [0]
 
-    def step(s):
-        res = halo_b200.acquire_batch(feat, P, A, cfg, gt, s["active"], s["selected"], s["active_mask"], want_picks=distributed)
-        if distributed:
-            pool.gather_round_delta(res["n_picked"], res["picks"], gt, replica, B * world, cfg.radius_k)
-        return res
+    def step(s, k):
+        """Step k of the job = batch (k mod R) of this rank's shard; after a round's last batch, its exchange."""
+        j = k % R
+        b = sizes[j]
+        res = halo_b200.acquire_batch(feat[:b], P, A, cfg, gt[:b], s["active"][:b], s["selected"][:b], s["active_mask"][:b],
+                                      want_picks=True)
+        ex.pack(j * B, res["picks"], res["n_picked"], gt[:b])
+        launches[0] += KERNELS_PER_STEP + 1
+        if j == R - 1:
+            ex.exchange(replica, counts)     # side stream: overlaps the next round's first batch
+            launches[0] += 1
+        return res, b
 
     for i in range(args.warmup):
-        res = step(state[i % n_state])
+        res, _ = step(state[i % n_state], i)
+    ex.wait()
     torch.cuda.synchronize()
     picks_ok = int(res["n_picked"].min().item()) if args.warmup else None
     for s in state:
         reset(s)
+    launches[0] = 0
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
@@ -311,26 +426,31 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
-    done = 0
+    done, images = 0, 0
     while done < args.steps:
         chunk = min(n_state, args.steps - done)
         for j in range(chunk):
-            res = step(state[j])
+            res, b = step(state[j], args.warmup + done + j)
+            images += b
         done += chunk
         if done < args.steps:  # recycle the state planes (outside the hot path; counted in the timed region)
             for j in range(min(n_state, args.steps - done)):
                 reset(state[j])
+    ex.wait()                  # the last exchange in flight belongs to the timed steps
     ev1.record()
     torch.cuda.synchronize()
     if distributed:
         dist.barrier()
     clocks = sampler.finish()
     ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    img_all = torch.tensor([images], dtype=torch.float64, device=dev)
     if distributed:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(img_all, op=dist.ReduceOp.SUM)
     ms_total = float(ms.item())
-    px_step = B * H * W * world
-    value = px_step * args.steps / (ms_total / 1e3) / 1e6
+    px_total = float(img_all.item()) * H * W
+    value = px_total / (ms_total / 1e3) / 1e6
+    timed_launches = launches[0]
 
     # ---- roofline of the dominant kernel (K1, fused head), timed alone on its launch stream ----
     roof = None
@@ -351,19 +471,22 @@ def run_ours(args):
         k_ms = k0.elapsed_time(k1) / reps
         alg_bytes = 4.0 * C * B * H * W  # features read once; SURVEY 8(d): radius/entropy planes are not algorithmic
         achieved = alg_bytes / (k_ms / 1e3) / 1e9
-        traffic = None
-        try:  # DRAM bytes per launch of this kernel from the committed ncu --set full capture (scaled per image)
-            with open(os.path.join(ROOT, "profiles", "r1n_traffic.json")) as f:
-                traffic = float(json.load(f)["dram_bytes_per_image"]) * B
-        except Exception:
-            traffic = None
+        traffic, traffic_src = traffic_from_profiles(B)
         roof = {"bound": "hbm", "kernel": "head_fwd_tc_kernel (K1 fused head, tcgen05)", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
-                "traffic_source": "profiles/r1n_traffic.json (ncu dram__bytes_read+write per launch)", "peak_source": peak_src,
+                "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
-                "step_frac": round((4.0 * C + 13) * px_step / world * args.steps / (ms_total / 1e3) / 1e9 / peak, 4)}
+                "step_frac": round((4.0 * C + 13) * px_total / world / (ms_total / 1e3) / 1e9 / peak, 4)}
     if distributed:
         dist.barrier()
+
+    # ---- the real round: the whole pool, sharded, ONE exchange, replicas checked against each other ----
+    full_round = None
+    del replica
+    if not args.no_round:
+        full_round = run_full_round(shard, P, A, cfg, world, distributed, dev)
+        shard.fill(lo, min(lo + B, hi))
+    torch.cuda.empty_cache()
 
     # ---- the other acquisition configurations of BASELINE.json / SURVEY 8(d), short runs on the same resident batch ----
     others = None
@@ -389,9 +512,10 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(B), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": (KERNELS_PER_STEP + (2 if distributed else 0)) * args.steps,  # + round_delta pack / apply
-            "picks_per_image": picks_ok, "other_configs": others, "train_step": train,
-            "round_seconds_at_this_rate": round(w["pool_images"] * H * W / (value * 1e6), 4),
+            "gpu_launches": timed_launches,
+            "picks_per_image": picks_ok, "round": full_round, "other_configs": others, "train_step": train,
+            "step_schedule": {"batches_per_round_per_gpu": R, "images_per_batch": sizes, "exchange": "one packed all-gather "
+                              "per round (after its last batch, on a side stream)" if distributed else "none (one GPU)"},
         }
         emit(line)
     if distributed:
@@ -552,6 +676,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the configs[4] fwd+bwd side measurement")
     ap.add_argument("--no-side-configs", action="store_true", help="skip the 911-pick and configs[3] side measurements")
+    ap.add_argument("--no-round", action="store_true", help="skip the full 2 975-image round (run once after the timed steps)")
     args = ap.parse_args()
     claim_stdout()
     if args.impl == "reference":

@@ -53,6 +53,10 @@ _SIGNATURES = {
     "halo_select_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "halo_round_delta_pack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "halo_round_delta_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "halo_round_row_bytes": (_sz, [_i, _i]),
+    "halo_round_rows_pack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "halo_round_rows_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "halo_checksum64": (_i, [_vp, _sz, ctypes.c_ulonglong, _vp, _i, _vp]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

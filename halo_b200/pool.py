@@ -92,36 +92,178 @@ def shard_range(n_items, rank, world):
     return start, start + base + (1 if rank < extra else 0)
 
 
-def acquire_pool(provider, n_images, P, A, cfg, *, batch_size=8, group=None, gather=True, device=None):
-    """Run one acquisition round over a pool of `n_images` images sharded by image over the ranks of `group`.
+def acquire_pool(provider, n_images, P, A, cfg, *, batch_size=148, group=None, gather=True, device=None, masks=None,
+                 exchange=None, keep_local=True, verify=False):
+    """Run one acquisition round over a pool of `n_images` images sharded by image over the ranks of `group`
+    (the reference's loop over the target pool, core/active/build.py:92, which it runs on rank 0 alone,
+    core/train_learners.py:307-326).
 
-    provider(lo, hi) -> dict(feat (b,C,H,W) fp32, gt, active, selected, active_mask (b,H,W) uint8), tensors on
-    this rank's device for global image indices [lo, hi).  Returns dict with this rank's planes and, when
-    `gather`, the all-gathered `n_picked` (n_images,) and `active_mask` (n_images,H,W) on every rank."""
+    provider(lo, hi) -> dict(feat (b,C,H,W) fp32, gt, active, selected, active_mask (b,H,W) uint8), tensors on this
+    rank's device for global image indices [lo, hi); the three state planes are updated in place.
+    Every batch runs K1 -> K2 -> K3 and packs its picks into this shard's row buffer; there is NO collective and no host
+    synchronisation until the shard is done.  Then ONE all-gather of the packed rows (on a side stream) and every rank
+    replays all rows onto `masks`, its (n_images,H,W) uint8 replica of the pool's label masks (allocated, all 255, when not
+    given; labels of earlier rounds stay).  Returns dict(rank, world, range, n_picked (n_images,) int32, active_mask
+    (n_images,H,W) [, *_local planes when keep_local] [, checksum, replicas_agree when verify])."""
     import torch.distributed as dist
 
     distributed = dist.is_available() and dist.is_initialized()
     rank = dist.get_rank(group) if distributed else 0
     world = dist.get_world_size(group) if distributed else 1
     lo, hi = shard_range(n_images, rank, world)
-    counts, masks, actives, selecteds = [], [], [], []
+    counts, lmasks, actives, selecteds = [], [], [], []
+    ex = exchange
     for b0 in range(lo, hi, batch_size):
         b1 = min(b0 + batch_size, hi)
         item = provider(b0, b1)
-        res = acquire_batch(item["feat"], P, A, cfg, item["gt"], item["active"], item["selected"], item["active_mask"])
-        counts.append(res["n_picked"])
-        masks.append(item["active_mask"])
-        actives.append(item["active"])
-        selecteds.append(item["selected"])
+        H, W = item["feat"].shape[-2:]
+        if gather and ex is None:
+            ex = RoundExchange(n_images, H, W, cfg.regions_per_image(H, W), cfg.radius_k, item["feat"].device, group=group)
+        res = acquire_batch(item["feat"], P, A, cfg, item["gt"], item["active"], item["selected"], item["active_mask"],
+                            want_picks=gather)
+        if gather:
+            ex.pack(b0 - lo, res["picks"], res["n_picked"], item["gt"])
+        if keep_local:
+            counts.append(res["n_picked"])
+            lmasks.append(item["active_mask"])
+            actives.append(item["active"])
+            selecteds.append(item["selected"])
     out = {"rank": rank, "world": world, "range": (lo, hi)}
     if counts:
         out["n_picked_local"] = torch.cat(counts)
-        out["active_mask_local"] = torch.cat(masks)
+        out["active_mask_local"] = torch.cat(lmasks)
         out["active_local"] = torch.cat(actives)
         out["selected_local"] = torch.cat(selecteds)
     if gather:
-        out.update(gather_round(out.get("n_picked_local"), out.get("active_mask_local"), n_images, group=group,
-                                device=device))
+        if ex is None:   # this rank owns no image (world > n_images) and was given no exchange: it still joins the gather
+            raise ValueError("acquire_pool: a rank that owns no image needs `exchange=RoundExchange(...)` (it cannot "
+                             "infer the image size)")
+        if masks is None:
+            masks = torch.full((n_images, ex.H, ex.W), 255, dtype=torch.uint8, device=ex.device)
+        n_picked = torch.zeros((n_images,), dtype=torch.int32, device=ex.device)
+        ex.exchange(masks, n_picked)
+        ex.wait()
+        out["n_picked"], out["active_mask"] = n_picked, masks
+        if verify:
+            out["checksum"], out["replicas_agree"] = ex.verify(masks, n_picked)
+    return out
+
+
+class RoundExchange:
+    """The one exchange at the end of a sharded round: preallocated packed rows, ONE all-gather, replay.
+
+    Per pool image one row [count | picks[cap] | window labels] (`halo_round_row_bytes`): 13 B per pick for 3x3 regions,
+    59 KB per 1280x640 image at 4 552 picks instead of the 819 KB mask plane.  `cap` comes from the configuration
+    (`AcquisitionConfig.regions_per_image`), so nothing is negotiated between the ranks and nothing synchronises with the
+    host.  `pack` runs on the caller's stream right after a batch's selection; `exchange` runs the all-gather and the
+    replay on a side stream behind an event, so it overlaps whatever the caller enqueues next; `wait` joins it.
+    `pack_fn` / `apply_fn` default to the CUDA entry points; the world_size-2 gloo tests (no GPU) pass the oracle's
+    restatement to exercise the sharding and the collective on CPU tensors."""
+
+    def __init__(self, n_images, H, W, cap, active_radius, device, *, group=None, pack_fn=None, apply_fn=None):
+        import torch.distributed as dist
+
+        self.group = group
+        self.distributed = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if self.distributed else 0
+        self.world = dist.get_world_size(group) if self.distributed else 1
+        self.n_images, self.H, self.W = int(n_images), int(H), int(W)
+        self.cap, self.r = max(int(cap), 1), int(active_radius)
+        self.device = torch.device(device)
+        self.per = (self.n_images + self.world - 1) // self.world
+        k2 = (2 * self.r + 1) ** 2
+        self.row_bytes = (4 + 4 * self.cap + self.cap * k2 + 15) // 16 * 16
+        self.pack_fn, self.apply_fn = pack_fn or pack_rows, apply_fn or apply_rows
+        # zeroed once: padding rows keep count = 0 for ever, real rows are rewritten by every round's pack
+        self.rows_local = torch.zeros((self.per, self.row_bytes), dtype=torch.uint8, device=self.device)
+        self.rows_all = (torch.empty((self.world * self.per, self.row_bytes), dtype=torch.uint8, device=self.device)
+                         if self.distributed else self.rows_local)
+        self.row_image = _row_maps(self.n_images, self.world, self.device)[0]
+        self.cuda = self.device.type == "cuda"
+        self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
+        self.done = torch.cuda.Event() if self.cuda else None
+
+    def pack(self, local_row, picks, n_picked, gt):
+        """Rows [local_row, local_row + b) of this shard <- the picks of a batch of b images (caller's stream)."""
+        b = picks.shape[0]
+        self.pack_fn(self.rows_local[local_row:local_row + b], picks, n_picked, gt, self.cap, self.r)
+
+    def exchange(self, masks, n_picked_out):
+        """All-gather the shard rows (one collective) and replay every rank's rows onto `masks` / `n_picked_out`."""
+        import torch.distributed as dist
+
+        def run():
+            if self.distributed:
+                dist.all_gather_into_tensor(self.rows_all, self.rows_local, group=self.group)
+            self.apply_fn(masks, self.row_image, self.rows_all, n_picked_out, self.cap, self.r)
+
+        if self.cuda:
+            self.side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self.side):
+                run()
+                self.done.record(self.side)
+        else:
+            run()
+
+    def wait(self):
+        if self.cuda:
+            torch.cuda.current_stream(self.device).wait_event(self.done)
+
+    def bytes_per_rank(self):
+        return self.per * self.row_bytes
+
+    def verify(self, masks, n_picked, checksum_fn=None):
+        """64-bit checksum of (masks, n_picked) on this rank and whether every rank holds the same one.
+        Synchronises with the host: call it outside timed regions."""
+        import torch.distributed as dist
+
+        cs = (checksum_fn or checksum64)(masks, n_picked)
+        agree = True
+        if self.distributed:
+            mine = cs.view(torch.int64).reshape(1)
+            allc = torch.empty((self.world,), dtype=torch.int64, device=mine.device)
+            dist.all_gather_into_tensor(allc, mine, group=self.group)
+            agree = bool((allc == allc[0]).all().item())
+        return int(cs.view(torch.int64).item()) & 0xFFFFFFFFFFFFFFFF, agree
+
+
+def pack_rows(rows, picks, n_picked, gt, cap, active_radius):
+    """`halo_round_rows_pack`: rows (b,row_bytes) uint8 view <- picks (b,stride) int32, n_picked (b,), gt (b,H,W)."""
+    nat.require_cuda(picks, "picks")
+    lib = nat.load()
+    b, stride = picks.shape
+    H, W = gt.shape[-2:]
+    with torch.cuda.device(picks.device):
+        rc = lib.halo_round_rows_pack(nat.ptr(picks), nat.ptr(n_picked), nat.ptr(gt), nat.ptr(rows), b, int(cap), stride, H, W,
+                                      int(active_radius), nat.stream_of(picks))
+    nat.check(rc, "halo_round_rows_pack")
+
+
+def apply_rows(masks, row_image, rows, n_picked_out, cap, active_radius):
+    """`halo_round_rows_apply`: replay packed rows onto masks (n_images,H,W) uint8 and scatter the counts."""
+    nat.require_cuda(masks, "masks")
+    lib = nat.load()
+    H, W = masks.shape[-2:]
+    with torch.cuda.device(masks.device):
+        rc = lib.halo_round_rows_apply(nat.ptr(masks), nat.ptr(row_image), nat.ptr(rows), nat.ptr(n_picked_out), rows.shape[0],
+                                       int(cap), H, W, int(active_radius), nat.stream_of(masks))
+    nat.check(rc, "halo_round_rows_apply")
+
+
+def checksum64(masks, n_picked):
+    """Device uint64 (stored in an int64 tensor) checksum of the masks followed by the counts (`halo_checksum64`)."""
+    nat.require_cuda(masks, "masks")
+    lib = nat.load()
+    out = torch.empty((1,), dtype=torch.int64, device=masks.device)
+    m = masks.contiguous()
+    c = n_picked.contiguous()
+    with torch.cuda.device(masks.device):
+        st = nat.stream_of(masks)
+        rc = lib.halo_checksum64(nat.ptr(m), m.numel() * m.element_size(), 0, nat.ptr(out), 0, st)
+        nat.check(rc, "halo_checksum64")
+        rc = lib.halo_checksum64(nat.ptr(c), c.numel() * c.element_size(), (m.numel() * m.element_size() + 7) // 8, nat.ptr(out),
+                                 1, st)
+        nat.check(rc, "halo_checksum64")
     return out
 
 
@@ -141,8 +283,10 @@ def gather_round(n_picked_local, mask_local, n_images, *, group=None, device=Non
     n_local = hi - lo
     if mask_local is not None:
         dev, hw = mask_local.device, tuple(mask_local.shape[1:])
-    else:
-        dev, hw = torch.device(device or "cpu"), None
+    else:   # a rank that owns no image: NCCL needs CUDA tensors, gloo CPU ones
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
+        dev, hw = torch.device(device), None
     # agree on the plane shape (a rank may own zero images when world > n_images)
     shape_t = torch.tensor(list(hw) if hw else [0, 0], dtype=torch.int64, device=dev)
     dist.all_reduce(shape_t, op=dist.ReduceOp.MAX, group=group)
@@ -196,14 +340,15 @@ def apply_round_delta(masks, row_image, picks, n_picked, lab, active_radius):
     return masks
 
 
-def gather_round_delta(n_picked_local, picks_local, gt_local, masks, n_images, active_radius, *, group=None,
+def gather_round_delta(n_picked_local, picks_local, gt_local, masks, n_images, active_radius, *, group=None, cap=None,
                        pack=pack_round_delta, apply=apply_round_delta):
     """Compact form of `gather_round`: all-gather (pick counts, picks, window labels) -- 13 B per pick for 3x3 regions
     instead of H*W bytes per image -- and replay them onto `masks` (n_images,H,W) uint8, this rank's replica of the
     pool's label masks (the labels of earlier rounds stay).  Works without a process group (single shard) too.
     `pack` / `apply` are the two CUDA entry points above; the world_size-2 gloo test, which has no GPU, passes the
     oracle's restatement of them (oracle/delta.py) to exercise the sharding and the collective on CPU tensors.
-    Returns {"n_picked": (n_images,) int32, "active_mask": masks}."""
+    Superseded on the hot path by `RoundExchange` (one packed all-gather, preallocated, side stream); kept as the
+    three-tensor form the round-1 tests pin.  Returns {"n_picked": (n_images,) int32, "active_mask": masks}."""
     import torch.distributed as dist
 
     distributed = dist.is_available() and dist.is_initialized()
@@ -213,11 +358,14 @@ def gather_round_delta(n_picked_local, picks_local, gt_local, masks, n_images, a
     lo, hi = shard_range(n_images, rank, world)
     n_local = hi - lo
     dev = masks.device
-    cap = picks_local.shape[1] if picks_local is not None else 0
-    if distributed:   # a rank may own zero images when world > n_images: agree on the pick capacity
-        cap_t = torch.tensor([cap], dtype=torch.int64, device=dev)
-        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX, group=group)
-        cap = int(cap_t[0])
+    if cap is None:   # the pick capacity is the per-image budget, known from the configuration: pass it to skip this
+        cap = picks_local.shape[1] if picks_local is not None else 0
+        if distributed:   # (kept for callers that do not: a rank may own zero images, so the ranks must agree -- host sync)
+            cap_t = torch.tensor([cap], dtype=torch.int64, device=dev)
+            dist.all_reduce(cap_t, op=dist.ReduceOp.MAX, group=group)
+            cap = int(cap_t[0])
+    if cap == 0:
+        return {"n_picked": torch.zeros((n_images,), dtype=torch.int32, device=dev), "active_mask": masks}
     k2 = (2 * int(active_radius) + 1) ** 2
     cnt_pad = torch.zeros((per,), dtype=torch.int32, device=dev)
     pk_pad = torch.full((per, cap), -1, dtype=torch.int32, device=dev)

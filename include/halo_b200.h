@@ -200,6 +200,27 @@ int halo_round_delta_pack(const int* picks, const int* n_picked, const uint8_t* 
 int halo_round_delta_apply(uint8_t* masks, const int* row_image, const int* picks, const int* n_picked,
                            const uint8_t* lab, int rows, int cap, int H, int W, int active_radius, halo_stream_t stream);
 
+
+/* ---- packed round rows: the ONE exchange at the end of a sharded round (the reference runs the round on
+ * rank 0 alone, core/train_learners.py:307-326, so this has no reference counterpart beyond build.py:58-62) ------------
+ * One row per pool image, row_bytes = halo_round_row_bytes(cap, a) (a multiple of 16):
+ *     [ int32 count ][ int32 picks[cap] ][ uint8 lab[cap][(2a+1)^2] ][ pad ]
+ * A shard packs its images' rows into one buffer (pack may be called once per batch with `rows` pointing at the batch's
+ * first row), all-gathers that buffer ONCE, and every rank replays all rows onto its replica of the pool's masks.
+ *   pack : picks [N,pick_stride] i32, n_picked [N] i32 (as written by halo_select_*), gt [N,H,W] u8 -> rows [N,row_bytes]
+ *   apply: rows [n_rows,row_bytes]; row j belongs to pool image row_image[j] (< 0: padding row, skipped);
+ *          masks [n_images,H,W] u8 receives the labels; n_picked_out [n_images] i32 | NULL receives the counts. */
+size_t halo_round_row_bytes(int cap, int active_radius);
+int halo_round_rows_pack(const int* picks, const int* n_picked, const uint8_t* gt, uint8_t* rows, int N, int cap,
+                         int pick_stride, int H, int W, int active_radius, halo_stream_t stream);
+int halo_round_rows_apply(uint8_t* masks, const int* row_image, const uint8_t* rows, int* n_picked_out, int n_rows,
+                          int cap, int H, int W, int active_radius, halo_stream_t stream);
+/* Position-sensitive 64-bit checksum of a device buffer (sum of 8-byte words times odd position weights, mod 2^64;
+ * order-independent, so bitwise reproducible): ranks compare it after the exchange to prove their replicas agree.
+ * word_offset chains several buffers as if concatenated; accumulate != 0 adds into *out instead of overwriting it. */
+int halo_checksum64(const void* data, size_t nbytes, unsigned long long word_offset, unsigned long long* out,
+                    int accumulate, halo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -187,3 +187,66 @@ def test_gather_round_delta_world2_gloo(tmp_path, n_images):
         keep = ~touched[:, 0, 5]
         assert bool((got[:, 0, 5][keep] == 3).all())   # the earlier round's label survives where this round wrote nothing
     assert torch.equal(outs[0]["delta"]["active_mask"], outs[1]["delta"]["active_mask"])
+
+
+def test_packed_rows_oracle_roundtrip_cpu():
+    """oracle/delta.py restatement of halo_round_rows_pack / _apply: rows -> masks equals the dense result."""
+    for r in (0, 1, 2):
+        gt, picks, cnt, dense = _delta_case(5, 9, 13, 7, r, seed=10 + r)
+        rb = odelta.row_bytes(7, r)
+        assert rb % 16 == 0 and rb >= 4 + 4 * 7 + 7 * (2 * r + 1) ** 2
+        rows = torch.randint(0, 255, (5, rb), dtype=torch.uint8)      # stale bytes past `count` must never matter
+        odelta.pack_rows(rows, picks, cnt, gt, 7, r)
+        masks = torch.full((6, 9, 13), 255, dtype=torch.uint8)
+        got_cnt = torch.full((6,), -7, dtype=torch.int32)
+        odelta.apply_rows(masks, torch.tensor([1, 2, 3, 4, 5], dtype=torch.int32), rows, got_cnt, 7, r)
+        assert torch.equal(masks[1:], dense) and bool((masks[0] == 255).all())
+        assert got_cnt.tolist() == [-7] + cnt.tolist()
+    a = odelta.checksum64(torch.arange(100, dtype=torch.uint8).reshape(4, 5, 5), torch.tensor([1, 2, 3], dtype=torch.int32))
+    b = torch.arange(100, dtype=torch.uint8).reshape(4, 5, 5)
+    b[3, 4, 4] ^= 1
+    assert int(a) != int(odelta.checksum64(b, torch.tensor([1, 2, 3], dtype=torch.int32)))   # position-sensitive
+    assert int(a) != int(odelta.checksum64(torch.arange(100, dtype=torch.uint8).reshape(4, 5, 5),
+                                           torch.tensor([1, 3, 2], dtype=torch.int32)))
+
+
+def _exchange_worker(rank, world, port, n_images, tmp):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, W, cap, r = 8, 12, 6, 1
+        gt, picks, cnt, dense = _delta_case(n_images, H, W, cap, r, seed=3)
+        lo, hi = pool.shard_range(n_images, rank, world)
+        ex = pool.RoundExchange(n_images, H, W, cap, r, "cpu", pack_fn=odelta.pack_rows, apply_fn=odelta.apply_rows)
+        assert ex.per == (n_images + world - 1) // world and ex.row_bytes == odelta.row_bytes(cap, r)
+        agree = []
+        for rnd in range(2):     # the exchange object is reused round after round (buffers allocated once)
+            masks = torch.full((n_images, H, W), 255, dtype=torch.uint8)
+            n_picked = torch.zeros((n_images,), dtype=torch.int32)
+            for b0 in range(lo, hi, 2):           # two batches per shard, packed as they finish
+                b1 = min(b0 + 2, hi)
+                ex.pack(b0 - lo, picks[b0:b1], cnt[b0:b1], gt[b0:b1])
+            ex.exchange(masks, n_picked)
+            ex.wait()
+            cs, ok = ex.verify(masks, n_picked, checksum_fn=odelta.checksum64)
+            agree.append(ok)
+        torch.save({"masks": masks, "n_picked": n_picked, "dense": dense, "cnt": cnt, "checksum": cs, "agree": agree},
+                   os.path.join(tmp, "x%d.pt" % rank))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_images", [5, 1, 4])
+def test_round_exchange_world2_gloo(tmp_path, n_images):
+    """ONE packed all-gather at the end of the round: every rank ends with the dense masks and counts of the whole pool,
+    and the cross-rank checksum agrees (n_images=1: rank 1 owns no image and still joins the exchange)."""
+    world = 2
+    mp.spawn(_exchange_worker, args=(world, _free_port(), n_images, str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(os.path.join(str(tmp_path), "x%d.pt" % r)) for r in range(world)]
+    for o in outs:
+        assert torch.equal(o["masks"], o["dense"]) and torch.equal(o["n_picked"], o["cnt"])
+        assert o["agree"] == [True, True]
+    assert outs[0]["checksum"] == outs[1]["checksum"]
