@@ -27,6 +27,7 @@ SELECT_KEEP_SCORE = 0x1
 
 ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = -1, -2, -3, -4
 PATH_FWD_TC, PATH_FWD_CUDA_CORE, PATH_BWD_PIX_TC, PATH_BWD_PIX_CUDA_CORE, PATH_BWD_DW_TC, PATH_BWD_DW_CUDA_CORE = 1, 2, 4, 8, 16, 32
+PATH_BWD_STREAM_TC, PATH_BWD_RECOMPUTE = 64, 128
 ABI_VERSION = 2
 
 _vp, _i, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
@@ -37,9 +38,10 @@ _SIGNATURES = {
     "halo_last_path": (_i, []),
     "halo_source_hash": (ctypes.c_char_p, []),
     "halo_head_workspace_bytes": (_sz, [_i, _i]),
-    "halo_head_fwd": (_i, [_vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "halo_head_saved_rows": (_i, [_i, _i, _i, _i]),
+    "halo_head_fwd": (_i, [_vp, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "halo_head_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "halo_head_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
+    "halo_head_bwd": (_i, [_vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "halo_expmap0_project": (_i, [_vp, _vp, _i, _f, _i, _i, _i, _i, _vp]),
     "halo_ball_norm": (_i, [_vp, _i, _f, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "halo_radius_f64": (_i, [_vp, _i, _f, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -100,7 +102,8 @@ def last_error():
 
 _PATH_NAMES = ((PATH_FWD_TC, "fwd:tcgen05"), (PATH_FWD_CUDA_CORE, "fwd:cuda_core"), (PATH_BWD_PIX_TC, "bwd_pix:tcgen05"),
                (PATH_BWD_PIX_CUDA_CORE, "bwd_pix:cuda_core"), (PATH_BWD_DW_TC, "bwd_dw:tcgen05"),
-               (PATH_BWD_DW_CUDA_CORE, "bwd_dw:cuda_core"))
+               (PATH_BWD_DW_CUDA_CORE, "bwd_dw:cuda_core"), (PATH_BWD_STREAM_TC, "bwd:stream_tcgen05"),
+               (PATH_BWD_RECOMPUTE, "bwd:recompute"))
 
 
 def last_path():

@@ -10,6 +10,7 @@
 // Reductions over pixels are two-stage with a fixed order (per-CTA partials, then one finalize block per
 // class), so gradients are bitwise reproducible for a given grid size.
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "head_common.cuh"
@@ -386,7 +387,7 @@ extern "C" size_t halo_head_bwd_workspace_bytes(int N, int C, int O, int H, int 
   bwd_grids(N, H * W, &pg, &dg);
   size_t b = ((size_t)CPAD * KP + 4 * OP) * 4;          // packed parameters
   b = (b + 255) / 256 * 256;
-  b += (size_t)N * KP * H * W * 4;                       // G planes
+  b += (size_t)N * (KP + 1) * H * W * 4;                 // G planes (two-kernel paths) or recomputed saved planes (streaming path)
   b = (b + 255) / 256 * 256;
   (void)pg;
   b += (size_t)sm_count() * 2 * 3 * OP * 4;              // class-scalar partials (one slot per CTA of either pixel pass)
@@ -416,9 +417,9 @@ static int launch_bwd(const BwdArgs& a, bool vec, size_t smem, int pix_grid, int
   return launch_status("head_bwd_dw_kernel");
 }
 
-extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, float c, const float* dlogits, float* dfeat,
-                             float* dP, float* dA, int N, int C, int O, int H, int W, void* ws, size_t ws_bytes,
-                             halo_stream_t stream) {
+extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, float c, const float* dlogits,
+                             const float* saved, float* dfeat, float* dP, float* dA, int N, int C, int O, int H, int W,
+                             void* ws, size_t ws_bytes, halo_stream_t stream) {
   HALO_CHECK_ARG(feat && P && A && dlogits && dfeat && dP && dA, "halo_head_bwd: NULL pointer");
   HALO_CHECK_ARG(N > 0 && C > 0 && O > 0 && H > 0 && W > 0 && c > 0.f, "halo_head_bwd: bad dims / curvature");
   if (O > 32) {
@@ -438,7 +439,7 @@ extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, 
   float* wpack = (float*)(w8 + off);
   off += ((size_t)CPAD * KP + 4 * OP) * 4; off = (off + 255) / 256 * 256;
   float* G = (float*)(w8 + off);
-  off += (size_t)N * KP * HW * 4; off = (off + 255) / 256 * 256;
+  off += (size_t)N * (KP + 1) * HW * 4; off = (off + 255) / 256 * 256;   // G planes, or the saved planes (KP + 1 rows)
   float* cls_part = (float*)(w8 + off);
   off += (size_t)sm_count() * 2 * 3 * OP * 4; off = (off + 255) / 256 * 256;
   float* dw_part = (float*)(w8 + off);
@@ -466,7 +467,31 @@ extern "C" int halo_head_bwd(const float* feat, const float* P, const float* A, 
   const int cblocks = CP / 256;
   int cls_grid = pix_grid;
   const char* force_cc = getenv("HALO_BWD_CUDA_CORE");  // parity tests pin the fp32 CUDA-core pixel pass
-  if (!(force_cc && force_cc[0] == '1') && head_bwd_tc_supported(C, O, H, W, feat, dfeat)) {
+  const char* force_two = getenv("HALO_BWD_TWO_KERNEL");  // parity tests pin the round-1 two-kernel tensor-core path
+  const bool pinned = (force_cc && force_cc[0] == '1') || (force_two && force_two[0] == '1');
+  if (saved != nullptr && halo_head_saved_rows(C, O, H, W) == 0) {
+    set_error("halo_head_bwd: saved planes given for a shape halo_head_saved_rows() does not support");
+    return HALO_ERR_BAD_ARG;
+  }
+  if (!pinned && head_bwd_stream_supported(C, O, H, W, feat, dfeat) &&
+      head_tc_supported(HALO_FEAT_TANGENT_F32, C, O, H, W, feat)) {
+    // streaming backward (head_bwd_stream_tc.cu): the features are read once for du and dW.  Without saved planes the
+    // contractions are recomputed first by the forward kernel in contraction-only mode (one more pass over the features).
+    const float* sv = saved;
+    if (sv == nullptr) {
+      HeadArgs fa;
+      memset(&fa, 0, sizeof(fa));
+      fa.feat = feat; fa.ws = wpack; fa.saved = G;
+      fa.N = N; fa.C = C; fa.CPAD = CPAD; fa.O = O; fa.HW = HW;
+      fa.hc = make_head_consts(c);
+      rc = head_fwd_tc_launch(fa, wpack, wtc, st);
+      if (rc) return rc;
+      sv = G;
+    }
+    dw_grid = cls_grid = head_bwd_stream_grid(N, HW);
+    note_path(HALO_PATH_BWD_STREAM_TC | (saved ? 0 : HALO_PATH_BWD_RECOMPUTE), true);
+    rc = head_bwd_stream_launch(feat, dlogits, sv, dfeat, dw_part, cls_part, wpack, w2, c, N, C, CPAD, O, H, W, CP, dw_grid, st);
+  } else if (!(force_cc && force_cc[0] == '1') && head_bwd_tc_supported(C, O, H, W, feat, dfeat)) {
     // pixel pass on the tensor cores (head_bwd_tc.cu); the weight-gradient GEMM below is shared
     rc = head_pack_tc_launch(wpack, wtc, C, CPAD, O, st);
     if (rc) return rc;

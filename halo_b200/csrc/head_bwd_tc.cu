@@ -480,6 +480,11 @@ __global__ void head_pack_bwd_planes_kernel(const float* __restrict__ std_pack, 
   }
 }
 
+int head_pack_bwd_planes_launch(const float* std_pack, float* w2, int C, int OP, cudaStream_t st) {
+  head_pack_bwd_planes_kernel<<<(2 * OP * C + 255) / 256, 256, 0, st>>>(std_pack, w2, C, OP);
+  return launch_status("head_pack_bwd_planes_kernel");
+}
+
 // ---- host side -----------------------------------------------------------------------------------------
 bool head_bwd_tc_supported(int C, int O, int H, int W, const void* feat, const void* dfeat) {
   if (C % BT_BK != 0 || C > 256 || C < 2 * BT_BK) return false;  // >= 2 pipeline stages per tile (sN2 hand-over, see converters)
@@ -516,9 +521,8 @@ int head_bwd_tc_launch(const float* feat, const float* dlogits, float* dfeat, fl
     return HALO_ERR_CUDA;
   }
   const int OP = head_op_pad(O), NP = round_up(2 * OP, 16), HW = H * W;
-  head_pack_bwd_planes_kernel<<<(2 * OP * C + 255) / 256, 256, 0, st>>>(std_pack, w2, C, OP);
   {
-    int rc = launch_status("head_pack_bwd_planes_kernel");
+    int rc = head_pack_bwd_planes_launch(std_pack, w2, C, OP, st);
     if (rc) return rc;
   }
   CUtensorMap tmap;

@@ -281,6 +281,7 @@ struct HeadArgs {
   float* pixunc;
   uint8_t* label;
   float* stats;
+  float* saved;   // [N][2*OP+1][HW] | NULL: the contractions S_k, T_k (rows k, OP+k; k < O) and |u|^2 (row 2*OP) for the backward
   const uint8_t* gt;
   int pixunc_mode, label_mode, norm_mode;
   int N, C, CPAD, O, HW;

@@ -280,8 +280,17 @@ extern "C" size_t halo_head_workspace_bytes(int O, int C) {
   return std_bytes + head_tc_pack_floats(O, C) * sizeof(float);
 }
 
+extern "C" int halo_head_saved_rows(int C, int O, int H, int W) {
+  if (C <= 0 || O <= 0 || H <= 0 || W <= 0) return 0;
+  // shapes both the tensor-core forward and the streaming backward take (pointer alignment is checked per call)
+  const void* aligned = reinterpret_cast<const void*>(uintptr_t(256));
+  if (!head_tc_shape_ok(HALO_FEAT_TANGENT_F32, C, O, H, W, aligned)) return 0;
+  if (!head_bwd_stream_shape_ok(C, O, H, W, aligned, aligned)) return 0;
+  return 2 * head_op_pad(O) + 1;
+}
+
 extern "C" int halo_head_fwd(const void* feat, int feat_kind, const float* P, const float* A, float c, float* logits,
-                             float* radius, float* pixunc, uint8_t* label, float* stats, const uint8_t* gt,
+                             float* radius, float* pixunc, uint8_t* label, float* stats, float* saved, const uint8_t* gt,
                              int pixunc_mode, int label_mode, int norm_mode, int N, int C, int O, int H, int W,
                              void* ws, size_t ws_bytes, halo_stream_t stream) {
   HALO_CHECK_ARG(feat && P && A, "halo_head_fwd: feat/P/A must not be NULL");
@@ -307,6 +316,11 @@ extern "C" int halo_head_fwd(const void* feat, int feat_kind, const float* P, co
   const int OP = head_op_pad(O), CPAD = round_up(C, HEAD_U);
   const size_t smem = ((size_t)CPAD * 2 * OP + 4 * OP) * sizeof(float);
   const bool use_tc = !no_tc && head_tc_supported(feat_kind, C, O, H, W, feat);
+  if (saved != nullptr && (!use_tc || halo_head_saved_rows(C, O, H, W) == 0)) {
+    set_error("halo_head_fwd: saved planes are written by the tensor-core path only (halo_head_saved_rows(C=%d,O=%d,H=%d,W=%d) "
+              "is 0, or the features are unaligned / not raw fp32)", C, O, H, W);
+    return HALO_ERR_UNSUPPORTED;
+  }
   if (!use_tc && smem > 200 * 1024) {
     set_error("halo_head_fwd: C=%d x O=%d class parameters (%zu B) exceed the shared-memory tile", C, O, smem);
     return HALO_ERR_UNSUPPORTED;
@@ -318,7 +332,7 @@ extern "C" int halo_head_fwd(const void* feat, int feat_kind, const float* P, co
 
   HeadArgs a;
   a.feat = feat; a.ws = (const float*)ws; a.logits = logits; a.radius = radius; a.pixunc = pixunc; a.label = label;
-  a.stats = stats; a.gt = gt; a.pixunc_mode = pixunc_mode; a.label_mode = label_mode; a.norm_mode = norm_mode;
+  a.stats = stats; a.saved = saved; a.gt = gt; a.pixunc_mode = pixunc_mode; a.label_mode = label_mode; a.norm_mode = norm_mode;
   a.N = N; a.C = C; a.CPAD = CPAD; a.O = O; a.HW = H * W;
   a.tiles_per_img = (a.HW + HEAD_THREADS * HEAD_PIX - 1) / (HEAD_THREADS * HEAD_PIX);
   a.total_tiles = a.tiles_per_img * N;

@@ -302,6 +302,21 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       if (lane == 0) mbar_arrive(&acc_empty[g]);
 
       const bool live = (p < HW);
+      if (a.saved != nullptr && live) {
+        // training forward: keep the contractions for the streaming backward (head_bwd_stream_tc.cu), which then reads
+        // the features ONCE (164 B per pixel saved here against a second 4*C-byte pass over u there)
+        float* sv = a.saved + (size_t)n * (2 * OP + 1) * HW + p;
+#pragma unroll
+        for (int k = 0; k < OP; ++k) {
+          if (k < a.O) {
+            __stcs(sv + (size_t)k * HW, S[k]);
+            __stcs(sv + (size_t)(OP + k) * HW, T[k]);
+          }
+        }
+        __stcs(sv + (size_t)(2 * OP) * HW, n2);
+      }
+      if (a.logits == nullptr && a.radius == nullptr && a.pixunc == nullptr && a.label == nullptr && a.stats == nullptr)
+        continue;   // contraction-only launch (backward called without saved planes)
       const PixelScalars ps = tangent_scalars(n2, hc);
       float l[OP];
 #pragma unroll
@@ -389,14 +404,17 @@ int head_tc_np(int O) {
 }
 
 bool head_tc_supported(int feat_kind, int C, int O, int H, int W, const void* feat) {
+  return head_tc_shape_ok(feat_kind, C, O, H, W, feat) && get_encode_fn() != nullptr;
+}
+
+bool head_tc_shape_ok(int feat_kind, int C, int O, int H, int W, const void* feat) {
   if (feat_kind != HALO_FEAT_TANGENT_F32) return false;
   if (C % TC_BK != 0 || C > 256 || C < TC_BK) return false;
   if (O > 32) return false;
   if (((long long)H * W) % 4 != 0) return false;          // TMA global stride must be a multiple of 16 bytes
   if ((reinterpret_cast<uintptr_t>(feat) & 15) != 0) return false;
   const TcSmemLayout L = tc_smem_layout(head_tc_np(O), head_op_pad(O), C);
-  if (L.total > 225 * 1024) return false;
-  return get_encode_fn() != nullptr;
+  return L.total <= 225 * 1024;
 }
 
 int head_pack_tc_launch(const float* std_pack, float* wtc, int C, int CPAD, int O, cudaStream_t st) {

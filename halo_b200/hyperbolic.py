@@ -39,15 +39,17 @@ def _as_u8(t, name):
 
 
 def head_forward(feat, P, A, c=1.0, *, kind="tangent", want_logits=True, want_radius=False, want_pixunc=False,
-                 want_label=False, want_stats=False, gt=None, pixunc_mode="entropy", label_mode="argmax",
-                 norm_mode="radius", tensor_cores=True):
+                 want_label=False, want_stats=False, want_saved=False, gt=None, pixunc_mode="entropy",
+                 label_mode="argmax", norm_mode="radius", tensor_cores=True):
     """One fused pass of the head over `feat` (N,C,H,W).  Returns a dict with the requested planes.
 
     kind: "tangent" (raw fp32 features, expmap fused) or "ball" (points already on the ball, fp32/fp64).
     tensor_cores=False keeps the contraction on the fp32 CUDA cores (the tcgen05 3xTF32 path is the default
     whenever the shape allows it: raw features, C % 32 == 0, C <= 256, H*W % 4 == 0).
     Wraps `halo_head_fwd` (include/halo_b200.h); replaces hyperbolic.py:28-39,74-83,120-188 and the
-    softmax-entropy / argmax prologue of floating_region.py:151-166."""
+    softmax-entropy / argmax prologue of floating_region.py:151-166.
+    want_saved: also return `saved`, the per-pixel contractions a training forward keeps for `head_backward` (None when
+    the shape cannot save: halo_head_saved_rows == 0)."""
     lib = nat.load()
     nat.require_cuda(feat, "feat")
     if feat.dim() != 4:
@@ -77,21 +79,28 @@ def head_forward(feat, P, A, c=1.0, *, kind="tangent", want_logits=True, want_ra
     pixunc = torch.empty((N, H, W), dtype=torch.float32, device=dev) if want_pixunc else None
     label = torch.empty((N, H, W), dtype=torch.uint8, device=dev) if want_label else None
     stats = torch.empty((N, 4), dtype=torch.float32, device=dev) if want_stats else None
+    saved = None
+    if want_saved and kind == "tangent" and tensor_cores:
+        rows = lib.halo_head_saved_rows(C, O, H, W)
+        if rows > 0 and feat.data_ptr() % 16 == 0:
+            saved = torch.empty((N, rows, H, W), dtype=torch.float32, device=dev)
     gt8 = _as_u8(gt, "gt")
     need = lib.halo_head_workspace_bytes(O, C)
     ws = nat.workspace.get(dev, "head", need)
     with torch.cuda.device(dev):
         rc = lib.halo_head_fwd(nat.ptr(feat), fk, nat.ptr(Pf), nat.ptr(Af), float(c), nat.ptr(logits), nat.ptr(radius),
-                               nat.ptr(pixunc), nat.ptr(label), nat.ptr(stats), nat.ptr(gt8), _PIXUNC[pixunc_mode],
+                               nat.ptr(pixunc), nat.ptr(label), nat.ptr(stats), nat.ptr(saved), nat.ptr(gt8), _PIXUNC[pixunc_mode],
                                _LABEL[label_mode], _NORM[norm_mode], N, C, O, H, W, nat.ptr(ws), ws.numel(),
                                nat.stream_of(feat))
     nat.check(rc, "halo_head_fwd")
-    out.update(logits=logits, radius=radius, pixunc=pixunc, label=label, stats=stats)
+    out.update(logits=logits, radius=radius, pixunc=pixunc, label=label, stats=stats, saved=saved)
     return out
 
 
-def head_backward(feat, P, A, c, dlogits):
-    """Fused backward of expmap + MLR (autograd of train_learners.py:362): returns (dfeat, dP, dA), all fp32."""
+def head_backward(feat, P, A, c, dlogits, saved=None):
+    """Fused backward of expmap + MLR (autograd of train_learners.py:362): returns (dfeat, dP, dA), all fp32.
+    saved: the planes `head_forward(..., want_saved=True)` returned for the same inputs (the backward then reads the
+    features once); None = recompute them."""
     lib = nat.load()
     nat.require_cuda(feat, "feat")
     feat = feat.float().contiguous()
@@ -107,7 +116,7 @@ def head_backward(feat, P, A, c, dlogits):
     need = lib.halo_head_bwd_workspace_bytes(N, C, O, H, W)
     ws = nat.workspace.get(dev, "head_bwd", need)
     with torch.cuda.device(dev):
-        rc = lib.halo_head_bwd(nat.ptr(feat), nat.ptr(Pf), nat.ptr(Af), float(c), nat.ptr(dlogits), nat.ptr(dfeat),
+        rc = lib.halo_head_bwd(nat.ptr(feat), nat.ptr(Pf), nat.ptr(Af), float(c), nat.ptr(dlogits), nat.ptr(saved), nat.ptr(dfeat),
                                nat.ptr(dP), nat.ptr(dA), N, C, O, H, W, nat.ptr(ws), ws.numel(), nat.stream_of(feat))
     nat.check(rc, "halo_head_bwd")
     return dfeat, dP, dA
@@ -118,18 +127,20 @@ class _FusedHead(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, u, P, A, c, handle):
-        res = head_forward(u, P, A, c, kind="tangent", want_logits=True, want_radius=True, want_stats=True)
+        res = head_forward(u, P, A, c, kind="tangent", want_logits=True, want_radius=True, want_stats=True, want_saved=True)
         if handle is not None:
             handle._radius = res["radius"]
             handle._radius_stats = res["stats"]
         ctx.save_for_backward(u, P, A)
+        ctx.saved_planes = res["saved"]     # S_k, T_k, |u|^2 per pixel (or None): the backward reads u once
         ctx.c = c
         return res["logits"]
 
     @staticmethod
     def backward(ctx, dlogits):
         u, P, A = ctx.saved_tensors
-        du, dP, dA = head_backward(u, P, A, ctx.c, dlogits)
+        du, dP, dA = head_backward(u, P, A, ctx.c, dlogits, saved=ctx.saved_planes)
+        ctx.saved_planes = None
         return du.to(u.dtype), dP.to(P.dtype), dA.to(A.dtype), None, None
 
 
@@ -271,7 +282,7 @@ def _norm_from_tangent(u, c, norm_mode):
     ws = nat.workspace.get(u.device, "head", lib.halo_head_workspace_bytes(1, C))
     with torch.cuda.device(u.device):
         rc = lib.halo_head_fwd(nat.ptr(u), nat.FEAT_TANGENT_F32, nat.ptr(z), nat.ptr(z), float(c), None, nat.ptr(n), None,
-                               None, nat.ptr(stats), None, 0, 0, _NORM[norm_mode], N, C, 1, H, W, nat.ptr(ws),
+                               None, nat.ptr(stats), None, None, 0, 0, _NORM[norm_mode], N, C, 1, H, W, nat.ptr(ws),
                                ws.numel(), nat.stream_of(u))
     nat.check(rc, "halo_head_fwd")
     return n, stats

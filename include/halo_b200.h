@@ -90,6 +90,8 @@ const char* halo_source_hash(void); /* "HALO_SRC_SHA256=<hex>": content hash of 
 #define HALO_PATH_BWD_PIX_CUDA_CORE 0x08
 #define HALO_PATH_BWD_DW_TC 0x10    /* head_bwd_dw_tc_kernel */
 #define HALO_PATH_BWD_DW_CUDA_CORE 0x20
+#define HALO_PATH_BWD_STREAM_TC 0x40 /* head_bwd_stream_kernel: du and dW from ONE pass over the features */
+#define HALO_PATH_BWD_RECOMPUTE 0x80 /* ... after recomputing the contractions (no saved planes were passed) */
 int halo_last_path(void);
 
 /* ---- Poincare-ball classifier head, forward -------------------------------------------------------
@@ -100,23 +102,31 @@ int halo_last_path(void);
  * Optional outputs (NULL = skip):
  *   logits [N,O,H,W] f32; radius [N,H,W] f32 (per norm_mode); pixunc [N,H,W] f32 (per pixunc_mode);
  *   label [N,H,W] u8 (per label_mode); stats [N,4] f32 = {min,max of the radius plane, unused, unused}
+ *   saved [N, halo_head_saved_rows(C,O,H,W), H*W] f32 | NULL: the per-pixel contractions <u,-p_k>, <u,a_k/|a_k|> and |u|^2 a
+ *   TRAINING forward keeps for halo_head_bwd (164 B per pixel at O = 19), so that the backward reads the features once.
+ *   Only shapes with halo_head_saved_rows() > 0 can save (HALO_ERR_UNSUPPORTED otherwise: call again with saved = NULL).
  *   gt [N,H,W] u8 is read only by HALO_PIXUNC_ONE_MINUS_PGT / HALO_LABEL_GT_FILLED.
  * ws: halo_head_workspace_bytes(O, C) bytes of device scratch (packed class parameters). */
 size_t halo_head_workspace_bytes(int O, int C);
+int halo_head_saved_rows(int C, int O, int H, int W); /* 2*round_up(O,4)+1, or 0 when the shape cannot save */
 int halo_head_fwd(const void* feat, int feat_kind, const float* P, const float* A, float c,
-                  float* logits, float* radius, float* pixunc, uint8_t* label, float* stats,
+                  float* logits, float* radius, float* pixunc, uint8_t* label, float* stats, float* saved,
                   const uint8_t* gt, int pixunc_mode, int label_mode, int norm_mode,
                   int N, int C, int O, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
 
 /* ---- head backward (core/train_learners.py:238,362,457,557: autograd through expmap + HyperMLR) ----
  *   feat [N,C,H,W] f32 raw features (HALO_FEAT_TANGENT_F32) ; dlogits [N,O,H,W] f32
+ *   saved: the planes halo_head_fwd wrote for the SAME feat / P / A / c, or NULL (the contractions are then recomputed
+ *          by one more pass over the features)
  *   dfeat [N,C,H,W] f32 ; dP, dA [O,C] f32 (overwritten, not accumulated)
- * Tensor-core kernels (tcgen05) run when C % 32 == 0, 64 <= C <= 256, O <= 24, H*W % 4 == 0 (weight gradient: C = 128 or
- * 256); other shapes take the fp32 CUDA-core kernels.  Reductions have a fixed order: results are bitwise reproducible
- * on a given device.  Environment knobs for A/B tests: HALO_BWD_CUDA_CORE=1, HALO_BWD_DW_CUDA_CORE=1 pin the fp32 paths. */
+ * Kernel selection (halo_last_path() reports it): C in {64,128,256}, O <= 24, H*W % 4 == 0 -> the streaming tensor-core
+ * kernel (du and dW from ONE pass over the features); else C % 32 == 0, 64 <= C <= 256, O <= 24 -> the two-kernel
+ * tensor-core path (pixel pass + weight gradient, the latter on tensor cores for C = 128 or 256); else fp32 CUDA-core
+ * kernels.  Reductions have a fixed order: results are bitwise reproducible on a given device.  Environment knobs for A/B
+ * tests: HALO_BWD_TWO_KERNEL=1, HALO_BWD_CUDA_CORE=1, HALO_BWD_DW_CUDA_CORE=1 pin the older paths. */
 size_t halo_head_bwd_workspace_bytes(int N, int C, int O, int H, int W);
 int halo_head_bwd(const float* feat, const float* P, const float* A, float c, const float* dlogits,
-                  float* dfeat, float* dP, float* dA, int N, int C, int O, int H, int W,
+                  const float* saved, float* dfeat, float* dP, float* dA, int N, int C, int O, int H, int W,
                   void* ws, size_t ws_bytes, halo_stream_t stream);
 
 /* ---- eager pieces of the head (callers that need the materialised tensors) --------------------------

@@ -51,15 +51,19 @@ def test_workspace_queries_are_pure():
 
 def test_bad_arguments_return_status_not_crash():
     lib = nat.load()
-    rc = lib.halo_head_fwd(None, 0, None, None, 1.0, None, None, None, None, None, None, 0, 0, 0, 1, 8, 19, 4, 4, None, 0, None)
+    rc = lib.halo_head_fwd(None, 0, None, None, 1.0, None, None, None, None, None, None, None, 0, 0, 0, 1, 8, 19, 4, 4, None, 0, None)
     assert rc == nat.ERR_BAD_ARG and "NULL" in nat.last_error()
     one = ctypes.c_void_p(16)  # never dereferenced: argument checks come first
-    rc = lib.halo_head_fwd(one, 0, one, one, -1.0, None, None, None, None, None, None, 0, 0, 0, 1, 8, 19, 4, 4, one, 1 << 20, None)
+    rc = lib.halo_head_fwd(one, 0, one, one, -1.0, None, None, None, None, None, None, None, 0, 0, 0, 1, 8, 19, 4, 4, one, 1 << 20, None)
     assert rc == nat.ERR_BAD_ARG and "curvature" in nat.last_error()
-    rc = lib.halo_head_fwd(one, 0, one, one, 1.0, None, None, None, None, None, None, 0, 0, 0, 1, 8, 40, 4, 4, one, 1 << 20, None)
+    rc = lib.halo_head_fwd(one, 0, one, one, 1.0, None, None, None, None, None, None, None, 0, 0, 0, 1, 8, 40, 4, 4, one, 1 << 20, None)
     assert rc == nat.ERR_UNSUPPORTED
-    rc = lib.halo_head_fwd(one, 0, one, one, 1.0, None, None, None, None, None, None, 0, 0, 0, 1, 8, 19, 4, 4, one, 8, None)
+    rc = lib.halo_head_fwd(one, 0, one, one, 1.0, None, None, None, None, None, None, None, 0, 0, 0, 1, 8, 19, 4, 4, one, 8, None)
     assert rc == nat.ERR_WORKSPACE
+    assert lib.halo_head_saved_rows(256, 19, 640, 1280) == 41 and lib.halo_head_saved_rows(64, 16, 8, 8) == 33
+    assert lib.halo_head_saved_rows(48, 19, 8, 8) == 0 and lib.halo_head_saved_rows(256, 28, 8, 8) == 0
+    rc = lib.halo_head_fwd(one, 0, one, one, 1.0, None, None, None, None, None, one, None, 0, 0, 0, 1, 48, 19, 4, 4, one, 1 << 20, None)
+    assert rc == nat.ERR_UNSUPPORTED and "saved" in nat.last_error()   # a shape that cannot save says so
     rc = lib.halo_score(one, one, None, None, None, None, None, 0, 0, 1, 4, 3, 19, one, None, one, 1, 8, 8, one, 64, None)
     assert rc == nat.ERR_BAD_ARG and "odd" in nat.last_error()
     rc = lib.halo_round_delta_pack(None, one, one, one, 1, 4, 8, 8, 1, None)

@@ -165,6 +165,7 @@ def test_backward_tensor_core_pixel_pass(shape, monkeypatch):
     args = (u.to(DEV), P.to(DEV), A.to(DEV), 1.0, dl.to(DEV))
     monkeypatch.delenv("HALO_BWD_CUDA_CORE", raising=False)
     monkeypatch.delenv("HALO_BWD_DW_CUDA_CORE", raising=False)
+    monkeypatch.setenv("HALO_BWD_TWO_KERNEL", "1")           # this test pins the round-1 two-kernel tensor-core path
     du, dP, dA = halo_b200.head_backward(*args)              # tcgen05 pixel pass + tcgen05 weight gradient (C = 128, 256)
     monkeypatch.setenv("HALO_BWD_DW_CUDA_CORE", "1")
     _, dP_mix, dA_mix = halo_b200.head_backward(*args)       # tcgen05 pixel pass + fp32 CUDA-core weight gradient
@@ -227,14 +228,24 @@ def test_backward_full_size_tensor_core_vs_cuda_core(shape, monkeypatch):
     dl = torch.randn((N, O, H, W), device=DEV, generator=torch.Generator(device=DEV).manual_seed(5)) * 1e-3
     monkeypatch.delenv("HALO_BWD_CUDA_CORE", raising=False)
     monkeypatch.delenv("HALO_BWD_DW_CUDA_CORE", raising=False)
-    du, dP, dA = halo_b200.head_backward(u, P, A, 1.0, dl)
-    du2, dP2, dA2 = halo_b200.head_backward(u, P, A, 1.0, dl)
+    monkeypatch.delenv("HALO_BWD_TWO_KERNEL", raising=False)
+    from halo_b200 import _native as nat
+    saved = halo_b200.head_forward(u, P, A, 1.0, want_logits=False, want_saved=True)["saved"]
+    assert saved is not None
+    du, dP, dA = halo_b200.head_backward(u, P, A, 1.0, dl, saved=saved)        # streaming kernel, features read once
+    assert nat.last_path() == ("bwd:stream_tcgen05",)
+    du2, dP2, dA2 = halo_b200.head_backward(u, P, A, 1.0, dl, saved=saved)
     assert torch.equal(du, du2) and torch.equal(dP, dP2) and torch.equal(dA, dA2)   # fixed-order reductions
+    du3, dP3, dA3 = halo_b200.head_backward(u, P, A, 1.0, dl)                  # same kernel after recomputing the contractions
+    assert nat.last_path() == ("bwd:stream_tcgen05", "bwd:recompute")
+    assert torch.equal(du, du3) and torch.equal(dP, dP3) and torch.equal(dA, dA3)
+    monkeypatch.setenv("HALO_BWD_TWO_KERNEL", "1")
+    du_tk, dP_tk, dA_tk = halo_b200.head_backward(u, P, A, 1.0, dl)            # round-1 two-kernel tensor-core path
+    assert nat.last_path()[0] == "bwd_pix:tcgen05"
     monkeypatch.setenv("HALO_BWD_CUDA_CORE", "1")
     du_cc, dP_cc, dA_cc = halo_b200.head_backward(u, P, A, 1.0, dl)
-    assert rel_err(du, du_cc) <= 1e-4
-    assert rel_err(dP, dP_cc) <= 1e-4
-    assert rel_err(dA, dA_cc) <= 1e-4
+    for a, b in ((du, du_cc), (dP, dP_cc), (dA, dA_cc), (du, du_tk), (dP, dP_tk), (dA, dA_tk)):
+        assert rel_err(a, b) <= 1e-4
 
 
 @pytest.mark.parametrize("shape", [(19, 256, 2, 2, 1), (19, 128, 2, 4, 3), (19, 256, 4, 4, 37), (3, 64, 2, 2, 5),
@@ -295,7 +306,41 @@ def test_last_path_reports_the_kernel_variant():
     halo_b200.head_forward(torch.randn(1, 48, 16, 16, device=DEV) * 0.1, P2, A2, 1.0)
     assert nat.last_path() == ("fwd:cuda_core",)
     dl = torch.randn(1, 19, 16, 16, device=DEV) * 1e-3
-    halo_b200.head_backward(u, P, A, 1.0, dl)
-    assert nat.last_path()[0] == "bwd_pix:tcgen05"
+    halo_b200.head_backward(u, P, A, 1.0, dl)                        # C = 64, the shipped HALO channel count: streaming kernel
+    assert nat.last_path() == ("bwd:stream_tcgen05", "bwd:recompute")
+    P3, A3 = synth.head_params(19, 96, seed=1, device=DEV)          # C = 96: two-kernel tensor-core pixel pass + CUDA-core dW
+    halo_b200.head_backward(torch.randn(1, 96, 16, 16, device=DEV) * 0.1, P3, A3, 1.0, dl)
+    assert nat.last_path() == ("bwd_pix:tcgen05", "bwd_dw:cuda_core")
     halo_b200.head_backward(torch.randn(1, 48, 16, 16, device=DEV) * 0.1, P2, A2, 1.0, dl)
     assert nat.last_path() == ("bwd_pix:cuda_core", "bwd_dw:cuda_core")
+
+
+@pytest.mark.parametrize("shape", [(19, 64, 24, 40, 2, 0.1), (19, 256, 16, 24, 1, 0.1), (16, 128, 20, 20, 2, 0.3),
+                                   (19, 256, 130, 126, 1, 0.1), (5, 64, 9, 12, 3, 1.0), (24, 128, 16, 16, 1, 0.2),
+                                   (19, 64, 160, 320, 1, 0.1), (8, 256, 12, 20, 1, 0.2), (19, 128, 2, 2, 5, 0.1)])
+def test_backward_streaming_kernel(shape, monkeypatch):
+    """K4s (head_bwd_stream_tc.cu): du and dW from ONE pass over the features, driven by the contractions the forward saved,
+    against fp64 autograd through the oracle -- every supported channel count (64 = the shipped HALO configs,
+    core/configs/defaults.py:14; 128; 256), class paddings 8 / 16 / 20 / 24, ragged tiles, tiny planes."""
+    from halo_b200 import _native as nat
+
+    for k in ("HALO_BWD_CUDA_CORE", "HALO_BWD_DW_CUDA_CORE", "HALO_BWD_TWO_KERNEL"):
+        monkeypatch.delenv(k, raising=False)
+    O, C, H, W, N, sigma = shape
+    P, A = synth.head_params(O, C, seed=13, dtype=torch.float64)
+    u = torch.stack([synth.image_features(i, C, H, W, sigma=sigma) for i in range(N)])
+    dl = torch.randn((N, O, H, W), generator=torch.Generator().manual_seed(3)) * 1e-3
+    du_ref, dP_ref, dA_ref = ohead.head_grads(u, P, A, dl, 1.0)
+    ud, Pd, Ad = u.to(DEV), P.to(DEV), A.to(DEV)
+    fwd = halo_b200.head_forward(ud, Pd, Ad, 1.0, want_logits=True, want_saved=True)
+    assert fwd["saved"] is not None and tuple(fwd["saved"].shape) == (N, 2 * ((O + 3) // 4 * 4) + 1, H, W)
+    logits_ref, _, _ = ohead.head_forward(u, P, A, 1.0)
+    assert rel_err(fwd["logits"], logits_ref) <= TOL                      # saving does not disturb the forward
+    du, dP, dA = halo_b200.head_backward(ud, Pd, Ad, 1.0, dl.to(DEV), saved=fwd["saved"])
+    assert nat.last_path() == ("bwd:stream_tcgen05",)
+    smooth = (~ohead.nonsmooth_pixels(u, P, 1.0, rel=1e-5))[:, None].to(du_ref.dtype)
+    assert smooth.mean() > 0.99
+    assert rel_err(du.cpu() * smooth, du_ref * smooth) <= 1e-4
+    assert rel_err(dP, dP_ref) <= 1e-4 and rel_err(dA, dA_ref) <= 1e-4
+    du2, dP2, dA2 = halo_b200.head_backward(ud, Pd, Ad, 1.0, dl.to(DEV))  # recompute instead of saved planes: same bits
+    assert torch.equal(du, du2) and torch.equal(dP, dP2) and torch.equal(dA, dA2)

@@ -29,7 +29,8 @@ def test_packed_rows_kernels_match_oracle():
         cfg = halo_b200.AcquisitionConfig(num_classes=O, radius_k=rk, mask_radius_k=3, budget=budget)
         P, A = synth.head_params(O, C, seed=2, device=DEV)
         d = synth.batch(0, B, C, O, H, W, device=DEV)
-        d["active"][1, :, 4:] = 1                             # image 1 cannot meet its budget (4 free columns): count < cap
+        d["active"][1] = 1
+        d["active"][1, :2, :2] = 0                            # image 1 cannot meet its budget (one pickable corner): count < cap
         res = halo_b200.acquire_batch(d["feat"], P, A, cfg, d["gt"], d["active"], d["selected"], d["active_mask"], want_picks=True)
         cap = cfg.regions_per_image(H, W)
         assert int(res["n_picked"][1]) < cap
