@@ -43,9 +43,9 @@ constexpr int BS_THREADS = 512;
 constexpr int BS_STAGE_BYTES = 128 * BS_CHUNK * 4;  // 16 KB: [128 ch x 32 px] (8 KB used when C = 64)
 constexpr int BS_MAX_STAGES = 8;
 #ifndef HALO_BS_DRAIN
-#define HALO_BS_DRAIN 4
+#define HALO_BS_DRAIN 8
 #endif
-constexpr int BS_DRAIN = HALO_BS_DRAIN;           // tiles per dW accumulator chain (48 MMAs per tile and channel block)
+constexpr int BS_DRAIN = HALO_BS_DRAIN;           // tiles per dW accumulator chain (48 MMAs per tile and channel block: 384 per chain)
 // TMEM columns (512): G hi|lo [0,96) | A buffer 0 [96,128) | D2 x2 [128,384) | A buffer 1 [384,416) | dW acc x2 [416,512)
 constexpr int BS_G_COL = 0, BS_A_COL0 = 96, BS_D2_COL = 128, BS_A_COL1 = 384, BS_ACC_COL = 416;
 
@@ -314,16 +314,17 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
         if (have) {
           for (int g = 0; g < nblk; ++g) {
             const uint32_t taddr = tmem_base + lane_addr + BS_ACC_COL + g * NP;
+            float* o = out + g * 128;
+            float prev[NR];   // the partial so far: all loads in flight together (one L2 round trip per drain, not NR)
+#pragma unroll
+            for (int k = 0; k < NR; ++k) prev[k] = (chain == 0) ? 0.f : __ldcg(o + (size_t)k * a.CP);
 #pragma unroll
             for (int c8 = 0; c8 < NR / 8; ++c8) {
               float m8[8];
               tmem_ld_x8(taddr + c8 * 8, m8);
               asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                float* o = out + (size_t)(c8 * 8 + e) * a.CP + g * 128;
-                *o = (chain == 0) ? m8[e] : *o + m8[e];
-              }
+              for (int e = 0; e < 8; ++e) __stcg(o + (size_t)(c8 * 8 + e) * a.CP, prev[c8 * 8 + e] + m8[e]);
             }
           }
         }
@@ -461,17 +462,26 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
         mbar_wait(&full[s], (uint32_t)(sc / NST) & 1u);
         mbar_wait(&d2_full[db], ((uint32_t)bc >> 1) & 1u);
         tc_fence_after();
-        const unsigned char* st = ring + (size_t)s * BS_STAGE_BYTES;
+        // shared-memory address of this lane's pixel in row 0 of the stage; row c adds c*128 and swaps the 16-byte unit by
+        // (c & 7) -- c0 is a multiple of 32, so the swap depends on e alone and every offset below is a literal
+        const uint32_t st = smem_u32(ring + (size_t)s * BS_STAGE_BYTES) + lane_e;
         const uint32_t d2 = tmem_base + lane_addr + BS_D2_COL + db * 128;
-        float* dg = dbase + (size_t)(g * 128) * HW;
+        float* pd = dbase + (size_t)(g * 128) * HW;
         for (int c0 = 0; c0 < cb; c0 += 32) {
-          float d[32];
-          tmem_ld_x32(d2 + c0, d);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float uv[32], d[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const float u = *reinterpret_cast<const float*>(st + (size_t)(c0 + e) * 128 + (((lane_q ^ (uint32_t)(e & 7)) << 4) | lane_e));
-            if (live) __stcs(dg + (size_t)(c0 + e) * HW, fmaf(alpha, u, d[e]));
+            const uint32_t addr = st + (uint32_t)(c0 + e) * 128u + ((lane_q ^ (uint32_t)(e & 7)) << 4);
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(uv[e]) : "r"(addr));
+          }
+          tmem_ld_x32(d2 + c0, d);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (live) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              __stcs(pd, fmaf(alpha, uv[e], d[e]));
+              pd += HW;
+            }
           }
         }
         tc_fence_before();
