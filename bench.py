@@ -563,33 +563,48 @@ def run_side_configs(feat, gt, st, dev):
 
 
 def run_train_step(feat8, P, A, c, peak):
-    """configs[4]: hyperbolic MLR head fused fwd+bwd on a resident batch (8 x 1280x640 x 256-d, 19 classes, fp32).
-    Algorithmic bytes 12*C + 8*O per pixel."""
+    """configs[4]: hyperbolic MLR head fused fwd+bwd on a resident batch (8 x 1280x640 x 256-d, 19 classes, fp32), as the
+    autograd Function runs it: the training forward writes the logits AND keeps the per-pixel contractions (164 B per
+    pixel), the streaming backward reads them, dlogits and the features ONCE and writes du (+ dP, dA).
+    Algorithmic bytes 12*C + 8*O per pixel.  Beside it: the same step at C = 64, the channel count every
+    shipped HALO config uses (core/configs/defaults.py:14), where the per-pixel math, not HBM, bounds the step."""
     import halo_b200
+    from halo_b200 import _native as nat
+    from halo_b200 import synth
 
+    def measure(feat, P, A):
+        B, C, H, W = feat.shape
+        O = P.shape[0]
+        dl = torch.randn((B, O, H, W), device=feat.device, generator=torch.Generator(device=feat.device).manual_seed(7)) * 1e-3
+
+        def step():
+            r = halo_b200.head_forward(feat, P, A, c, want_logits=True, want_saved=True)
+            return halo_b200.head_backward(feat, P, A, c, dl, saved=r["saved"])
+
+        for _ in range(3):
+            step()
+        path = list(nat.last_path())
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        t0.record()
+        for _ in range(reps):
+            step()
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / reps
+        px = B * H * W
+        alg = (12.0 * C + 8.0 * O) * px
+        return {"workload": "head fwd+bwd, batch %d x %dx%d x %d-d, %d classes, fp32" % (B, W, H, C, O),
+                "ms_per_step": round(ms, 3), "Mpixel/s": round(px / ms / 1e3, 1), "algorithmic_GB_per_step": round(alg / 1e9, 2),
+                "GB/s": round(alg / ms / 1e6, 1), "frac_of_hbm_peak": round(alg / ms / 1e6 / peak, 4), "backward_path": path,
+                "gpu_launches_per_step": 8}
+
+    out = measure(feat8, P, A)
+    out["workload"] = "BASELINE.json configs[4]: " + out["workload"]
     B, C, H, W = feat8.shape
-    O = P.shape[0]
-    dl = torch.randn((B, O, H, W), device=feat8.device, generator=torch.Generator(device=feat8.device).manual_seed(7)) * 1e-3
-
-    def step():
-        halo_b200.head_forward(feat8, P, A, c, want_logits=True)
-        return halo_b200.head_backward(feat8, P, A, c, dl)
-
-    for _ in range(3):
-        step()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
-    t0.record()
-    for _ in range(reps):
-        step()
-    t1.record()
-    torch.cuda.synchronize()
-    ms = t0.elapsed_time(t1) / reps
-    px = B * H * W
-    alg = (12.0 * C + 8.0 * O) * px
-    return {"workload": "BASELINE.json configs[4]: head fwd+bwd, batch %d x %dx%d x %d-d, %d classes, fp32" % (B, W, H, C, O),
-            "ms_per_step": round(ms, 3), "Mpixel/s": round(px / ms / 1e3, 1), "algorithmic_GB_per_step": round(alg / 1e9, 2),
-            "GB/s": round(alg / ms / 1e6, 1), "frac_of_hbm_peak": round(alg / ms / 1e6 / peak, 4), "gpu_launches_per_step": 9}
+    P64, A64 = synth.head_params(P.shape[0], 64, seed=0, device=feat8.device)
+    out["c64"] = measure(feat8[:2].reshape(B, 64, H, W), P64, A64)   # the same bytes viewed as 8 images of 64 channels
+    return out
 
 
 def run_e2e(args, cfg, P, A, dev, rank, world, distributed):
