@@ -186,6 +186,31 @@ __device__ __forceinline__ void softmax_stats(const float (&l)[OP], int O, const
   label = (label_mode == HALO_LABEL_GT_FILLED) ? gtf : arg;
 }
 
+// the acquisition path's common case: entropy only, no label / ground truth.  No arg-max bookkeeping; padded classes carry
+// logit -3e38 (their exp and p*log p terms vanish by themselves), so the loops run without per-class predicates
+// (~60 instructions fewer per pixel at 19 classes: the epilogue warps are K1's critical role, profiles/r2_k1.md)
+template <int OP>
+__device__ __forceinline__ float softmax_entropy_only(const float (&l)[OP], const HeadConsts& hc) {
+  float mx = l[0];
+#pragma unroll
+  for (int k = 1; k < OP; ++k) mx = fmaxf(mx, l[k]);
+  float e[OP];
+  float Z = 0.f;
+#pragma unroll
+  for (int k = 0; k < OP; ++k) {
+    e[k] = fast_exp(l[k] - mx);
+    Z += e[k];
+  }
+  const float iz = fast_rcp(Z);
+  float ent = 0.f;
+#pragma unroll
+  for (int k = 0; k < OP; ++k) {
+    const float p = e[k] * iz;
+    ent -= p * fast_lg2(p + 1e-6f);
+  }
+  return ent * (0.69314718056f * hc.inv_log19);
+}
+
 // ---- analytic derivative of the epilogue (shared by the CUDA-core and tensor-core backward kernels) -----------
 struct PixelScalarGrads {
   float gamma, t2, omega;   // as in PixelScalars

@@ -321,8 +321,11 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       float l[OP];
 #pragma unroll
       for (int k = 0; k < OP; ++k) {
-        const float4 cl = reinterpret_cast<const float4*>(sCls)[k];
-        l[k] = mlr_logit(S[k], T[k], ps, cl.x, cl.y, cl.z, cl.w, hc);
+        l[k] = -3.0e38f;     // padded classes: skipped (warp-uniform), and invisible to the softmax below
+        if (k < OP - 3 || k < a.O) {
+          const float4 cl = reinterpret_cast<const float4*>(sCls)[k];
+          l[k] = mlr_logit(S[k], T[k], ps, cl.x, cl.y, cl.z, cl.w, hc);
+        }
       }
 #ifdef HALO_TC_VARIANTS
       if (a.debug_raw) {  // numerics probe: expose the raw contractions <u,a_hat_k> instead of the logits
@@ -344,8 +347,9 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
         int gtv = 255;
         if (a.gt != nullptr && live) gtv = a.gt[pix];
         float unc;
-        int lab;
-        softmax_stats<OP>(l, a.O, hc, a.pixunc_mode, a.label_mode, gtv, unc, lab);
+        int lab = 0;
+        if (a.label == nullptr && a.pixunc_mode == HALO_PIXUNC_ENTROPY) unc = softmax_entropy_only<OP>(l, hc);
+        else softmax_stats<OP>(l, a.O, hc, a.pixunc_mode, a.label_mode, gtv, unc, lab);
         if (live) {
           if (a.pixunc != nullptr) __stcs(a.pixunc + pix, unc);
           if (a.label != nullptr) a.label[pix] = (uint8_t)lab;
