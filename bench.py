@@ -501,6 +501,15 @@ def run_ours(args):
     if distributed:
         dist.barrier()
 
+    # ---- the drop-in path the Lightning learner calls, at the real pipeline shape (not the headline) ----
+    dropin = None
+    if rank == 0 and world == 1 and not args.no_dropin:
+        os.sched_setaffinity(0, all_cpus)
+        dropin = run_dropin(dev)
+        bind_to_gpu_numa_node(local)
+    if distributed:
+        dist.barrier()
+
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ----
     e2e = run_e2e(args, cfg, P, A, dev, rank, world, distributed)
     if rank == 0 and not args.no_cpu_baseline and world == 1:
@@ -513,7 +522,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(B), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": timed_launches,
-            "picks_per_image": picks_ok, "round": full_round, "other_configs": others, "train_step": train,
+            "picks_per_image": picks_ok, "round": full_round, "other_configs": others, "train_step": train, "dropin": dropin,
             "step_schedule": {"batches_per_round_per_gpu": R, "images_per_batch": sizes, "exchange": "one packed all-gather "
                               "per round (after its last batch, on a side stream)" if distributed else "none (one GPU)"},
         }
@@ -607,6 +616,109 @@ def run_train_step(feat8, P, A, c, peak):
     return out
 
 
+class _Features(dict):
+    """Stand-in for the image tensor of a loader item: the backbone is out of scope (BASELINE.json north_star), so the item
+    carries the decoder features the backbone would have produced; `.cuda()` / `.shape` / `.device` are what
+    RegionSelection touches (core/active/build.py:94,112)."""
+    shape = (1, 3, 640, 1280)
+    device = torch.device("cpu")
+
+    def cuda(self, non_blocking=False):
+        r = _Features({k: v.cuda(non_blocking=non_blocking) for k, v in self.items()})
+        r.device = next(iter(r.values())).device
+        return r
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def run_dropin(dev, n_images=24):
+    """The path the Lightning learner calls (core/train_learners.py:318-322): `RegionSelection(cfg, feature_extractor,
+    classifier, loader, round)` of the drop-in package over a fake loader at the REAL pipeline shape -- decoder features
+    160x320 (C = 64, the shipped REDUCED_CHANNELS), labels 1024x2048, 19 classes, 1 % budget per round (BUDGET 0.05 over 5
+    SELECT_ITER), entropy x radius, batch 1 -- including the int64 CPU planes the loader hands over, the fused up-sampling
+    in front of the score, the batched selection and the PNG + indicator files on disk.  Wall clock, host side included.
+    Beside it: the reference sequence (build.py:92-166) by the oracle on the host cores, on a bounded sample."""
+    import shutil
+    import tempfile
+
+    import halo_b200
+    from halo_b200 import synth
+
+    C, O, h, w, H, W = 64, 19, 160, 320, 1024, 2048
+    cfg = _Cfg(ACTIVE=_Cfg(RADIUS_K=1, MASK_RADIUS_K=5, BUDGET=0.05, SELECT_ITER=[0, 1, 2, 3, 4], UNCERTAINTY="entropy",
+                           PURITY="radius", K=100, NORMALIZE=True, VIZ_MASK=False),
+               MODEL=_Cfg(NUM_CLASSES=O, CURVATURE=1.0, HYPER=True))
+
+    class Head(torch.nn.Module):   # ASPP_Classifier_V2_Hyper.forward (core/models/classifier.py:365-379) on precomputed features
+        def __init__(self):
+            super().__init__()
+            self.mapper = halo_b200.HyperMapper(c=1.0)
+            self.conv_seg = halo_b200.HyperMLR(C, O, c=1.0)
+
+        def forward(self, x, size=None):
+            embed = self.mapper.expmap(x["out"], dim=1)
+            return self.conv_seg(embed.double()).float(), embed
+
+    head = Head().to(dev)
+    tmp = tempfile.mkdtemp(prefix="halo_dropin_")
+
+    def items(lo, hi):
+        out = []
+        for i in range(lo, hi):
+            out.append({"img": _Features({"out": synth.image_features(i, C, h, w, sigma=0.15)[None]}),
+                        "path_to_mask": [os.path.join(tmp, "m%d.png" % i)], "path_to_indicator": [os.path.join(tmp, "i%d.pth" % i)],
+                        "origin_mask": [torch.full((H, W), 255, dtype=torch.long)], "origin_label": [synth.image_labels(i, O, H, W).long()],
+                        "size": [(H, W)], "active": [torch.zeros((H, W), dtype=torch.bool)], "selected": [torch.zeros((H, W), dtype=torch.bool)]})
+        return out
+
+    try:
+        halo_b200.RegionSelection(cfg, torch.nn.Identity(), head, items(0, 4), round_number=1)      # warm-up
+        loader = items(4, 4 + n_images)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        halo_b200.RegionSelection(cfg, torch.nn.Identity(), head, loader, round_number=1)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        from PIL import Image
+        import numpy as np
+
+        labelled = int((np.array(Image.open(loader[0]["path_to_mask"][0])) != 255).sum())
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    res = {"workload": "drop-in RegionSelection, %d images: features %dx%dx%d -> labels %dx%d, %d classes, 1 %% budget per round "
+                       "(2 331 picks), batch 1, files written" % (n_images, C, h, w, H, W, O),
+           "ms_per_image": round(dt / n_images * 1e3, 2), "images/s": round(n_images / dt, 2),
+           "Mpixel/s_label_res": round(n_images * H * W / dt / 1e6, 1), "labelled_pixels_image0": labelled}
+    # reference sequence on the CPU (oracle port), one image
+    try:
+        from oracle import acquire as oacquire
+        from oracle import head as ohead
+        from oracle import select as oselect
+        import numpy as np
+
+        torch.set_num_threads(os.cpu_count() or 1)
+        P = head.conv_seg.P_MLR.detach().cpu().double()
+        A = head.conv_seg.A_MLR.detach().cpu().double()
+        u = synth.image_features(4, C, h, w, sigma=0.15)[None]
+        gt = synth.image_labels(4, O, H, W).long()
+        t1 = time.perf_counter()
+        lo, x, _ = ohead.head_forward(u, P, A, 1.0)
+        sc, _, _ = oacquire.upsampled_score(lo, x, (H, W), unc_type="entropy", pur_type="radius", normalize=True, ground_truth=None,
+                                            in_channels=O, size=3, ctor_purity_type="radius", K=100, c=1.0)
+        n_regions = int(np.ceil(H * W * 0.01 / 9))
+        oselect.select_sequential(sc, n_regions, 1, 5, torch.zeros((H, W), dtype=torch.bool), torch.zeros((H, W), dtype=torch.bool),
+                                  torch.full((H, W), 255, dtype=torch.int64), gt)
+        cpu_dt = time.perf_counter() - t1
+        res["cpu_reference"] = {"ms_per_image": round(cpu_dt * 1e3, 1), "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "1 image through oracle head + F.interpolate (fp64 embedding) + score + sequential "
+                                          "arg-max selection, no file I/O"}
+    except Exception as e:  # noqa: BLE001
+        res["cpu_reference"] = {"error": repr(e)[:200]}
+    return res
+
+
 def run_e2e(args, cfg, P, A, dev, rank, world, distributed):
     """Same metric through the public API from pinned HOST memory: per step the features, labels and mask state of
     `e2e_batch` images are copied host->device, scored and selected, and counts + updated masks copied back."""
@@ -691,6 +803,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the configs[4] fwd+bwd side measurement")
     ap.add_argument("--no-side-configs", action="store_true", help="skip the 911-pick and configs[3] side measurements")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in RegionSelection leg (fake loader, files on disk)")
     ap.add_argument("--no-round", action="store_true", help="skip the full 2 975-image round (run once after the timed steps)")
     args = ap.parse_args()
     claim_stdout()

@@ -75,12 +75,22 @@ def to_np_array(tensor):
     return np.array(tensor.cpu().numpy(), dtype=np.uint8)
 
 
+def _to_u8_device(t, device):
+    """Loader tensors arrive on the CPU as int64 / bool planes (cityscapes.py:274-286): narrow them to uint8 BEFORE the
+    host->device copy (8x fewer PCIe bytes than the reference's `.cuda()` of the int64 plane)."""
+    if t.is_cuda:
+        return t.to(torch.uint8)
+    return t.to(torch.uint8).to(device, non_blocking=True)
+
+
 def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_number):
     """Reference `RegionSelection` (build.py:71-186): one acquisition round over the target pool on this rank.
 
-    Same loader item contract (core/datasets/cityscapes.py:274-286) and on-disk side effects.  The per-image
-    body runs the CUDA path: classifier head (fused when the classifier was built with this package's
-    HyperMapper/HyperMLR), FloatingRegionScore, select_pixels_to_label."""
+    Same loader item contract (core/datasets/cityscapes.py:274-286) and on-disk side effects.  The per-image body runs
+    the CUDA path: classifier head (fused when the classifier was built with this package's HyperMapper/HyperMLR),
+    FloatingRegionScore with `score[active] = -inf` (:146) fused into its last pass, and the budgeted selection --
+    deferred and run for `ACTIVE.SELECT_BATCH` (optional key, default 8) images of equal size in one launch, because the
+    selection kernel gives each image one SM (images are independent: build.py:137-160 touches nothing shared)."""
     feature_extractor.eval()
     classifier.eval()
 
@@ -98,14 +108,31 @@ def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_
                        or purity_type in ["hyper", "radius", "euc_norm"]
                        or (uncertainty_type == "none" and cfg.MODEL.HYPER))
 
+    def optional(key, default):   # keys the reference's config does not define
+        try:
+            return int(getattr(cfg.ACTIVE, key))
+        except (AttributeError, KeyError):
+            return default
+
     # PNG encoding + torch.save leave the loop: same files, written by a thread pool from pinned
     # staging buffers; flushed before this function returns, as the caller expects (train_learners.py:318-322 reloads
     # the dataset right after)
-    try:
-        io_workers = int(cfg.ACTIVE.IO_WORKERS)   # optional key; the reference's config does not define it
-    except (AttributeError, KeyError):
-        io_workers = 4
-    writer = AsyncMaskWriter(workers=io_workers)
+    writer = AsyncMaskWriter(workers=optional("IO_WORKERS", 4))
+    select_batch = max(1, optional("SELECT_BATCH", 8))
+    pending = []   # images scored and waiting for the batched selection: (score, active, selected, mask, gt, paths)
+
+    def flush_pending():
+        if not pending:
+            return
+        size = tuple(pending[0][0].shape)
+        score = torch.stack([q[0] for q in pending])
+        act, sel, msk, gt = (torch.stack([q[k] for q in pending]) for k in (1, 2, 3, 4))
+        active_regions = math.ceil(size[0] * size[1] * active_budget / per_region_pixels)    # build.py:148-150
+        select_planes(score, act, sel, msk, gt, active_regions, active_radius, mask_radius, keep_score=True)
+        for j, q in enumerate(pending):
+            writer.write(msk[j], act[j], sel[j], q[5], q[6])                                  # build.py:162-166
+        pending.clear()
+
     with torch.no_grad(), writer:
         idx = 0
         for tgt_data in tgt_epoch_loader:
@@ -117,15 +144,16 @@ def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_
             if idx == 0:
                 feature_extractor.to(tgt_input.device)
                 classifier.to(tgt_input.device)
+            dev = tgt_input.device
             tgt_size = tgt_input.shape[-2:]
             tgt_out, decoder_out = classifier(feature_extractor(tgt_input), size=tgt_size)
 
             for i in range(len(origin_mask)):
-                active_mask = origin_mask[i].cuda(non_blocking=True)
-                ground_truth = origin_label[i].cuda(non_blocking=True)
                 size = (int(origin_size[i][0]), int(origin_size[i][1]))
-                active = active_indicator[i]
-                selected = selected_indicator[i]
+                active_mask = _to_u8_device(origin_mask[i], dev).reshape(size)
+                ground_truth = _to_u8_device(origin_label[i], dev).reshape(size)
+                active = _to_u8_device(active_indicator[i], dev).reshape(size)
+                selected = _to_u8_device(selected_indicator[i], dev).reshape(size)
 
                 out_i = tgt_out[i:i + 1]
                 emb = decoder_out[i:i + 1] if needs_embedding else None
@@ -133,20 +161,20 @@ def RegionSelection(cfg, feature_extractor, classifier, tgt_epoch_loader, round_
                     # already at label size (reference: F.interpolate to the same size is the identity)
                     score, _, _ = floating_region_score(out_i, decoder_out=emb, normalize=cfg.ACTIVE.NORMALIZE,
                                                         unc_type=uncertainty_type, pur_type=purity_type,
-                                                        ground_truth=ground_truth)
+                                                        ground_truth=ground_truth, active=active)
                 else:
                     # reference build.py:122-135 up-samples logits and (fp64) embedding -- possibly from different
                     # resolutions (classifier.py:556-557) -- THEN scores; fused here, nothing is materialised
                     score, _, _ = floating_region_score.forward_upsampled(
                         out_i, emb, size, normalize=cfg.ACTIVE.NORMALIZE, unc_type=uncertainty_type,
-                        pur_type=purity_type, ground_truth=ground_truth)
-                score[active.to(score.device)] = -float("inf")
-                active_regions = math.ceil(size[0] * size[1] * active_budget / per_region_pixels)
-                score, active, selected, active_mask = select_pixels_to_label(
-                    score, active_regions, active_radius, mask_radius, active, selected, active_mask, ground_truth)
-
-                writer.write(active_mask, active, selected, path2mask[i], path2indicator[i])   # build.py:162-166
+                        pur_type=purity_type, ground_truth=ground_truth, active=active)
+                if pending and tuple(pending[0][0].shape) != size:
+                    flush_pending()
+                pending.append((score, active, selected, active_mask, ground_truth, path2mask[i], path2indicator[i]))
+                if len(pending) >= select_batch:
+                    flush_pending()
             idx += 1
+        flush_pending()
 
     feature_extractor.train()
     classifier.train()

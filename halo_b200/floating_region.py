@@ -72,6 +72,15 @@ def score_planes(pixunc, radius, radius_stats, label, active, *, unc_mode, pur_m
     return score, imp, unc
 
 
+def _active_plane(active, N, H, W):
+    if active is None:
+        return None
+    nat.require_cuda(active, "active")
+    if active.dtype != torch.uint8:
+        active = active.to(torch.uint8)
+    return active.reshape(N, H, W).contiguous()
+
+
 def modes_for(unc_type, pur_type):
     """Map the reference's strings to the kernel modes (floating_region.py:70-92,158-202)."""
     if pur_type not in _KNOWN_PURITIES:
@@ -141,11 +150,13 @@ class FloatingRegionScore(nn.Module):
         return out, stats
 
     def forward(self, logit: torch.Tensor, decoder_out=None, unc_type: str = None, pur_type: str = None,
-                normalize: bool = False, ground_truth=None):
+                normalize: bool = False, ground_truth=None, active=None):
         """Compute region score, impurity and uncertainty (reference :129-217).
 
         logit: (1,O,H,W) (a batch (N,O,H,W) is accepted as an extension and returns (N,H,W) maps);
         decoder_out: PoincareEmbedding or (N,C,H,W) tensor on the ball (needed by 'radius'/'hyper'/'euc_norm').
+        active (extension): (N,H,W) / (H,W) uint8 device plane; score[active != 0] = -inf is fused into the last pass
+        (what `RegionSelection` does next, core/active/build.py:146).
         Returns (score, region_impurity, prediction_uncertainty), each (H,W)."""
         lib = nat.load()
         nat.require_cuda(logit, "logit")
@@ -186,15 +197,15 @@ class FloatingRegionScore(nn.Module):
         n_bins = self.K if pur_mode == nat.PUR_RADIUS_BINS else self.in_channels
         if pixunc is None and radius is None and r64 is None:  # "none"/"none": the kernel still needs a shape carrier
             pixunc = torch.zeros((N, H, W), dtype=torch.float32, device=dev)
-        score, imp, unc = score_planes(pixunc, radius, stats, label, None, unc_mode=unc_mode, pur_mode=pur_mode,
-                                       normalize=normalize, k=self.size, pk=self.purity_size, n_bins=n_bins,
-                                       want_impurity=True, radius64=r64, radius_stats64=st64)
+        score, imp, unc = score_planes(pixunc, radius, stats, label, _active_plane(active, N, H, W), unc_mode=unc_mode,
+                                       pur_mode=pur_mode, normalize=normalize, k=self.size, pk=self.purity_size,
+                                       n_bins=n_bins, want_impurity=True, radius64=r64, radius_stats64=st64)
         if N == 1:
             return score[0], imp[0], unc[0]
         return score, imp, unc
 
     def forward_upsampled(self, logit_lr, decoder_out_lr, size, unc_type=None, pur_type=None, normalize=False,
-                          ground_truth=None):
+                          ground_truth=None, active=None):
         """Score at label resolution from LOW-resolution logits and embedding (extension).
 
         Equivalent to the reference sequence of `RegionSelection` (core/active/build.py:122-144):
@@ -259,9 +270,9 @@ class FloatingRegionScore(nn.Module):
         n_bins = self.K if pur_mode == nat.PUR_RADIUS_BINS else self.in_channels
         if pixunc is None and radius is None:
             pixunc = torch.zeros((N, H, W), dtype=torch.float32, device=dev)
-        score, imp, unc = score_planes(pixunc, radius, stats, label, None, unc_mode=unc_mode, pur_mode=pur_mode,
-                                       normalize=normalize, k=self.size, pk=self.purity_size, n_bins=n_bins,
-                                       want_impurity=True, radius64=r64, radius_stats64=st64)
+        score, imp, unc = score_planes(pixunc, radius, stats, label, _active_plane(active, N, H, W), unc_mode=unc_mode,
+                                       pur_mode=pur_mode, normalize=normalize, k=self.size, pk=self.purity_size,
+                                       n_bins=n_bins, want_impurity=True, radius64=r64, radius_stats64=st64)
         if N == 1:
             return score[0], imp[0], unc[0]
         return score, imp, unc
