@@ -353,16 +353,20 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
       const int n = tile / a.tiles_per_img;
       const int p = (tile - n * a.tiles_per_img) * BS_BM + m;
       const bool live = (p < HW);
-      const float* dl = a.dlogits + (size_t)n * O * HW + p;
-      const float* sv = a.saved + (size_t)n * SVR * HW + p;
-      const float n2 = live ? __ldg(sv + (size_t)(2 * OP) * HW) : 0.f;
+      // dead lanes of a ragged tile read the image's last pixel (valid memory) and get zero upstream gradients, so every
+      // load below is unpredicated and every quantity they produce is an exact zero
+      const int pc = live ? p : HW - 1;
+      const float* pG = a.dlogits + (size_t)n * O * HW + pc;          // class k0 .. of the group being prefetched
+      const float* pS = a.saved + (size_t)n * SVR * HW + pc;
+      const float* pT = pS + (size_t)OP * HW;
+      const float n2 = __ldg(pS + (size_t)(2 * OP) * HW);
+      const size_t hw = (size_t)HW;
       float Sn[4], Tn[4], Gn[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const bool ok = live && e < O;
-        Sn[e] = ok ? __ldcs(sv + (size_t)e * HW) : 0.f;
-        Tn[e] = ok ? __ldcs(sv + (size_t)(OP + e) * HW) : 0.f;
-        Gn[e] = ok ? __ldcs(dl + (size_t)e * HW) : 0.f;
+        Sn[e] = __ldcs(pS + e * hw);
+        Tn[e] = __ldcs(pT + e * hw);
+        Gn[e] = (e < O) ? __ldcs(pG + e * hw) : 0.f;
       }
       const PixelScalarGrads ps = tangent_scalar_grads(n2, hc);
       float g_gamma = 0.f, g_t2 = 0.f, g_om = 0.f;
@@ -370,38 +374,60 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
 #pragma unroll 1
       for (int k0 = 0; k0 < OP; k0 += 4) {
         float Sc[4], Tc[4], Gc[4];
+        pS += 4 * hw; pT += 4 * hw; pG += 4 * hw;
+        const bool more = (k0 + 4 < OP);          // warp-uniform: the saved planes hold OP rows, dlogits only O
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          Sc[e] = Sn[e]; Tc[e] = Tn[e]; Gc[e] = Gn[e];
-          const int kn = k0 + 4 + e;
-          const bool ok = live && kn < O;
-          Sn[e] = ok ? __ldcs(sv + (size_t)kn * HW) : 0.f;
-          Tn[e] = ok ? __ldcs(sv + (size_t)(OP + kn) * HW) : 0.f;
-          Gn[e] = ok ? __ldcs(dl + (size_t)kn * HW) : 0.f;
+          Sc[e] = Sn[e]; Tc[e] = Tn[e]; Gc[e] = live ? Gn[e] : 0.f;
+          if (more) {
+            Sn[e] = __ldcs(pS + e * hw);
+            Tn[e] = __ldcs(pT + e * hw);
+            Gn[e] = (k0 + 4 + e < O) ? __ldcs(pG + e * hw) : 0.f;
+          }
         }
         float gS[4], gT[4];
+        float cs[16];     // class-scalar partials of the group: [class e][d_pp, d_an, d_pa], padded to 16
+#pragma unroll
+        for (int e = 0; e < 16; ++e) cs[e] = 0.f;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int k = k0 + e;
-          float d_pp = 0.f, d_an = 0.f, d_pa = 0.f;
           gS[e] = gT[e] = 0.f;
-          if (k < O) {   // warp-uniform
+          if (k < OP - 3 || k < O) {   // warp-uniform; a compile-time truth for all but the last three classes
             const float4 cl = reinterpret_cast<const float4*>(sCls)[k];
-            mlr_logit_grad(Gc[e], Sc[e], Tc[e], ps, cl.x, cl.y, cl.z, cl.w, hc, gS[e], gT[e], g_gamma, g_t2, g_om, d_pp, d_an,
-                           d_pa);
-            if (!live) { gS[e] = gT[e] = 0.f; }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              d_pp += __shfl_xor_sync(0xffffffffu, d_pp, o);
-              d_an += __shfl_xor_sync(0xffffffffu, d_an, o);
-              d_pa += __shfl_xor_sync(0xffffffffu, d_pa, o);
-            }
-            if (lane == 0) {
-              red[0 * OP + k] += d_pp;
-              red[1 * OP + k] += d_an;
-              red[2 * OP + k] += d_pa;
-            }
+            mlr_logit_grad(Gc[e], Sc[e], Tc[e], ps, cl.x, cl.y, cl.z, cl.w, hc, gS[e], gT[e], g_gamma, g_t2, g_om, cs[3 * e + 0],
+                           cs[3 * e + 1], cs[3 * e + 2]);
           }
+        }
+        // warp reduction of the 12 partials by recursive halving: at every step a lane hands half of its values to its
+        // partner and adds the partner's other half, so 8 + 4 + 2 + 1 + 1 shuffles replace 12 x 5 (fixed order: bitwise
+        // reproducible).  Afterwards lanes 2j and 2j+1 both hold the warp total of value j.
+        {
+          const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+          float r8[8], r4[4], r2[2], r1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float send = b4 ? cs[j] : cs[j + 8];
+            r8[j] = (b4 ? cs[j + 8] : cs[j]) + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float send = b3 ? r8[j] : r8[j + 4];
+            r4[j] = (b3 ? r8[j + 4] : r8[j]) + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float send = b2 ? r4[j] : r4[j + 2];
+            r2[j] = (b2 ? r4[j + 2] : r4[j]) + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          {
+            const float send = b1 ? r2[0] : r2[1];
+            r1 = (b1 ? r2[1] : r2[0]) + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          r1 += __shfl_xor_sync(0xffffffffu, r1, 1);
+          const int j = lane >> 1;             // value index: class e = j / 3 of the group, scalar t = j % 3
+          const int e = j / 3, t = j - 3 * e;
+          if ((lane & 1) == 0 && j < 12 && k0 + e < O) red[t * OP + k0 + e] += r1;
         }
         // park the group's gradients in statically indexed registers until the G buffers are free (see below)
 #pragma unroll
