@@ -14,7 +14,8 @@
 // One persistent 512-thread CTA per SM, per 128-pixel tile i:
 //   warps 8-11 / 12-15  two DERIVATIVE warpgroups on alternate tiles (thread = pixel = TMEM lane): saved S, T, |u|^2 and
 //                 dlogits -> gS, gT (kept in registers), alpha, class-scalar partials; once the previous tile has released
-//                 the G buffers: G as TF32 hi/lo into TMEM (A operand of the du GEMM) and into shared memory in the
+//                 the G buffers: G as TF32 hi/lo into TMEM (A operand of the du GEMM -- early, so that the first du GEMM of
+//                 the tile overlaps the previous tile's stream) and, pixel chunk by pixel chunk, into shared memory in the
 //                 K-major SWIZZLE_128B layout [n][px] (B operand of the dW GEMM).  The same warpgroup then runs the OUTPUT
 //                 pass of its tile: warp q takes the stages of pixel chunk q -- D2 from TMEM (its own lanes) + alpha*u with
 //                 u read from the stage in shared memory -> coalesced 128-byte du stores.
@@ -74,7 +75,7 @@ __host__ __device__ inline BsSmem bs_smem_layout(int NP, int OP, int C) {
   int st = (budget > L.ring_off + tail) ? (int)((budget - L.ring_off - tail) / BS_STAGE_BYTES) : 0;
   L.stages = st > BS_MAX_STAGES ? BS_MAX_STAGES : st;
   L.bar_off = L.ring_off + (size_t)L.stages * BS_STAGE_BYTES;
-  const int nbars = 2 * BS_MAX_STAGES + 3 + 4 + 4 + 2;
+  const int nbars = 2 * BS_MAX_STAGES + 2 + 2 * BS_NQ + 4 + 4 + 2;
   L.tmem_off = L.bar_off + (size_t)nbars * 8;
   L.cls_off = (L.tmem_off + 16 + 15) / 16 * 16;
   L.red_off = L.cls_off + (size_t)4 * OP * 4;
@@ -108,10 +109,11 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* full = bars;                          // [8] TMA bytes landed
   uint64_t* empty = bars + BS_MAX_STAGES;         // [8] 4 converter warps + the output warp of the stage's pixel chunk
-  uint64_t* g_ready = bars + 2 * BS_MAX_STAGES;   // G of a tile is in TMEM and shared memory
+  uint64_t* g_ready = bars + 2 * BS_MAX_STAGES;   // G of a tile is in TMEM (A operand of the du GEMMs)
   uint64_t* g_tmem_free = g_ready + 1;            // the du GEMMs of a tile have read G from TMEM
-  uint64_t* g_smem_free = g_ready + 2;            // the dW GEMMs of a tile have read G from shared memory
-  uint64_t* d2_full = g_ready + 3;                // [2]
+  uint64_t* gs_ready = g_ready + 2;               // [4] pixel chunk q of G is in shared memory (B operand of the dW GEMMs)
+  uint64_t* gs_free = gs_ready + BS_NQ;           // [4] the dW GEMMs of a tile have read chunk q
+  uint64_t* d2_full = gs_free + BS_NQ;            // [2]
   uint64_t* d2_empty = d2_full + 2;               // [2] the four output warps have read the buffer
   uint64_t* a_full = d2_empty + 2;                // [2]
   uint64_t* a_empty = a_full + 2;                 // [2]
@@ -135,7 +137,8 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 5); }
-    mbar_init(g_ready, 4); mbar_init(g_tmem_free, 1); mbar_init(g_smem_free, 1);
+    mbar_init(g_ready, 4); mbar_init(g_tmem_free, 1);
+    for (int q = 0; q < BS_NQ; ++q) { mbar_init(&gs_ready[q], 1); mbar_init(&gs_free[q], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], 4);
       mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1);
@@ -219,10 +222,10 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
         mbar_wait(acc_empty, (((uint32_t)(i / BS_DRAIN)) & 1u) ^ 1u);   // the previous chain has been drained
         tc_fence_after();
       }
-      mbar_wait(g_ready, (uint32_t)i & 1u);
       for (int g = 0; g < nblk; ++g) {
         const uint32_t acc = tb + BS_ACC_COL + g * NP;
         for (int q = 0; q < BS_NQ; ++q) {
+          if (g == 0) mbar_wait(&gs_ready[q], (uint32_t)i & 1u);   // chunk q of this tile's G has been written
           const uint32_t gq_hi = g_hi0 + (uint32_t)(q * NP * 128), gq_lo = g_lo0 + (uint32_t)(q * NP * 128);
 #pragma unroll
           for (int h = 0; h < 2; ++h, ++hc) {
@@ -242,16 +245,16 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
                 tc_mma_tf32_ts(acc, a_col + ks * 8, b_lo, idesc, 1u);
               }
               tc_commit(&a_empty[bf]);
+              if (h == 1 && g == nblk - 1) tc_commit(&gs_free[q]);   // last use of chunk q by this tile
             }
             __syncwarp();
           }
         }
       }
-      if (elect_one_sync()) {
-        tc_commit(g_smem_free);
-        if (ci == BS_DRAIN - 1 || i == my_tiles - 1) tc_commit(acc_full);
+      if (ci == BS_DRAIN - 1 || i == my_tiles - 1) {
+        if (elect_one_sync()) tc_commit(acc_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else if (warp >= 4 && warp < 8) {
     // =================== converters (thread = channel = TMEM lane) ===================
@@ -439,19 +442,21 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
         }
       }
       const float alpha = live ? 2.f * (g_gamma * ps.dgam + g_t2 * ps.dt2 + g_om * ps.dom) : 0.f;
-      // G buffers are single: wait until the GEMMs of the previous tile (the other warpgroup's) have read them
+      // The G buffers are single.  TMEM copy first, as soon as the du GEMMs of the previous tile (the other warpgroup's)
+      // have read theirs: the du GEMM of this tile's first channel block then runs while the previous tile is still
+      // streaming, and its D2 is waiting when this tile's first stage arrives.  The shared-memory copy follows chunk by
+      // chunk: warp wq owns pixel chunk wq and only waits for the previous tile's last dW GEMM on THAT chunk.
+      uint32_t sh[OP], sl[OP], th[OP], tl[OP];
+#pragma unroll
+      for (int k = 0; k < OP; ++k) {
+        sh[k] = cvt_rna_tf32(keepS[k]);
+        sl[k] = __float_as_uint(keepS[k] - __uint_as_float(sh[k]));
+        th[k] = cvt_rna_tf32(keepT[k]);
+        tl[k] = __float_as_uint(keepT[k] - __uint_as_float(th[k]));
+      }
       mbar_wait(g_tmem_free, ((uint32_t)i & 1u) ^ 1u);
-      mbar_wait(g_smem_free, ((uint32_t)i & 1u) ^ 1u);
       tc_fence_after();
       {
-        uint32_t sh[OP], sl[OP], th[OP], tl[OP];
-#pragma unroll
-        for (int k = 0; k < OP; ++k) {
-          sh[k] = cvt_rna_tf32(keepS[k]);
-          sl[k] = __float_as_uint(keepS[k] - __uint_as_float(sh[k]));
-          th[k] = cvt_rna_tf32(keepT[k]);
-          tl[k] = __float_as_uint(keepT[k] - __uint_as_float(th[k]));
-        }
         const uint32_t fg = tmem_base + lane_addr + BS_G_COL;
 #pragma unroll
         for (int k4 = 0; k4 < OP / 4; ++k4) {
@@ -460,7 +465,14 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
           tmem_st_x4(fg + NP + 4 * k4, *reinterpret_cast<uint32_t(*)[4]>(&sl[4 * k4]));
           tmem_st_x4(fg + NP + OP + 4 * k4, *reinterpret_cast<uint32_t(*)[4]>(&tl[4 * k4]));
         }
-        // shared-memory copy for the dW GEMM: chunk wq, row n, this lane's pixel (conflict-free: a warp writes one row)
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(g_ready);
+      mbar_wait(&gs_free[wq], ((uint32_t)i & 1u) ^ 1u);
+      {
+        // chunk wq, row n, this lane's pixel (conflict-free: a warp writes one 128-byte row per instruction)
         unsigned char* gq_hi = sG + (size_t)wq * NP * 128;
         unsigned char* gq_lo = gq_hi + L.g_plane;
 #pragma unroll
@@ -473,11 +485,9 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
           *reinterpret_cast<uint32_t*>(gq_lo + o_t) = tl[k];
         }
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores of G -> visible to the dW GEMM
-      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(g_ready);
+      if (lane == 0) mbar_arrive(&gs_ready[wq]);
 
       // ---- output pass of this tile: warp wq owns pixel chunk wq of every channel block ----
       float* dbase = a.dfeat + (size_t)n * C * HW + p;
