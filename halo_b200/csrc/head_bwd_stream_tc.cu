@@ -159,6 +159,13 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
   const int HW = a.HW;
   const int my_tiles = ((int)blockIdx.x < a.total_tiles) ? (a.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
+  // Register budget by role (setmaxnreg, warpgroup-wide, issued at the top of each role's region so that no control-flow
+  // merge follows it): the control warps give registers back, the derivative warpgroups -- 40 parked gradients + the
+  // class math + the output pass -- take 152 instead of the 128 a 512-thread CTA gets (128 x 80 + 128 x 128 + 256 x 152 = 65 536).
+  if (warp < 4) {
+#ifndef HALO_BS_NO_SETMAXNREG
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+#endif
   if (warp == 0) {
     // =================== TMA producer ===================
     int s = 0;
@@ -256,7 +263,8 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
         __syncwarp();
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  }
+  } else if (warp < 8) {
     // =================== converters (thread = channel = TMEM lane) ===================
     const int wq = warp & 3, ch = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
@@ -342,6 +350,9 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
     }
   } else if (warp >= 8) {
     // =================== derivative warpgroups (thread = pixel = TMEM lane), then the output pass of the tile ===========
+#ifndef HALO_BS_NO_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+#endif
     const int wg = (warp - 8) >> 2;                 // even / odd tiles
     const int wq = warp & 3, m = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
@@ -351,26 +362,38 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
     float* red = sRed + (size_t)(warp - 8) * 3 * OP;
     // byte offset of this lane's pixel inside a 128-byte SW128 row whose (row & 7) == r:  ((lane>>2) ^ r) << 4 | (lane&3) << 2
     const uint32_t lane_q = (uint32_t)lane >> 2, lane_e = ((uint32_t)lane & 3u) << 2;
-    for (int i = wg; i < my_tiles; i += 2) {
-      const int tile = blockIdx.x + i * gridDim.x;
+    // The first loads of a tile (|u|^2 and the first class group) are issued one own-tile ahead -- before the output pass of
+    // the previous one -- so the derivative math never starts by waiting a DRAM round trip (r2e profile: 10 % of this role).
+    const size_t hw = (size_t)HW;
+    float n2 = 0.f, Sn[4], Tn[4], Gn[4];
+    const float *pG = nullptr, *pS = nullptr, *pT = nullptr;
+    auto first_loads = [&](int it) {
+      const int tile = blockIdx.x + it * gridDim.x;
       const int n = tile / a.tiles_per_img;
       const int p = (tile - n * a.tiles_per_img) * BS_BM + m;
-      const bool live = (p < HW);
       // dead lanes of a ragged tile read the image's last pixel (valid memory) and get zero upstream gradients, so every
-      // load below is unpredicated and every quantity they produce is an exact zero
-      const int pc = live ? p : HW - 1;
-      const float* pG = a.dlogits + (size_t)n * O * HW + pc;          // class k0 .. of the group being prefetched
-      const float* pS = a.saved + (size_t)n * SVR * HW + pc;
-      const float* pT = pS + (size_t)OP * HW;
-      const float n2 = __ldg(pS + (size_t)(2 * OP) * HW);
-      const size_t hw = (size_t)HW;
-      float Sn[4], Tn[4], Gn[4];
+      // load is unpredicated and every quantity they produce is an exact zero
+      const int pc = (p < HW) ? p : HW - 1;
+      pG = a.dlogits + (size_t)n * O * HW + pc;          // class k0 .. of the group being prefetched
+      pS = a.saved + (size_t)n * SVR * HW + pc;
+      pT = pS + (size_t)OP * HW;
+      n2 = __ldg(pS + (size_t)(2 * OP) * HW);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         Sn[e] = __ldcs(pS + e * hw);
         Tn[e] = __ldcs(pT + e * hw);
         Gn[e] = (e < O) ? __ldcs(pG + e * hw) : 0.f;
       }
+    };
+    if (wg < my_tiles) first_loads(wg);
+    for (int i = wg; i < my_tiles; i += 2) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int n = tile / a.tiles_per_img;
+      const int p = (tile - n * a.tiles_per_img) * BS_BM + m;
+      const bool live = (p < HW);
+#ifdef HALO_BS_NO_PREFETCH
+      if (i != wg) first_loads(i);
+#endif
       const PixelScalarGrads ps = tangent_scalar_grads(n2, hc);
       float g_gamma = 0.f, g_t2 = 0.f, g_om = 0.f;
       float keepS[OP], keepT[OP];
@@ -488,6 +511,9 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores of G -> visible to the dW GEMM
       __syncwarp();
       if (lane == 0) mbar_arrive(&gs_ready[wq]);
+#ifndef HALO_BS_NO_PREFETCH
+      if (i + 2 < my_tiles) first_loads(i + 2);     // in flight under the output pass below
+#endif
 
       // ---- output pass of this tile: warp wq owns pixel chunk wq of every channel block ----
       float* dbase = a.dfeat + (size_t)n * C * HW + p;
