@@ -611,7 +611,58 @@ def run_train_step(feat8, P, A, c, peak):
     B, C, H, W = feat8.shape
     P64, A64 = synth.head_params(P.shape[0], 64, seed=0, device=feat8.device)
     out["c64"] = measure(feat8[:2].reshape(B, 64, H, W), P64, A64)   # the same bytes viewed as 8 images of 64 channels
+    out["fused_loss"] = run_loss_step(feat8.device, P.shape[0])
     return out
+
+
+def run_loss_step(dev, O):
+    """SURVEY 8f row 4 at the reference's training shape: logits 8 x O x 160x320 -> crop 640x1280 (classifier.py:556-557),
+    CrossEntropy(ignore 255) on 5 % labelled pixels + negative-learning loss, forward AND backward to the low-resolution
+    logits: `halo_seg_loss` (two kernels, nothing of size (N,O,H,W) materialised) beside the reference's torch sequence run
+    eagerly on the same GPU (F.interpolate -> softmax -> CE + NegativeLearningLoss -> autograd)."""
+    import torch.nn.functional as F
+
+    from halo_b200.losses import fused_seg_loss
+
+    N, h, w, H, W = 8, 160, 320, 640, 1280
+    g = torch.Generator(device=dev).manual_seed(11)
+    logits = torch.randn((N, O, h, w), device=dev, generator=g) * 3.0
+    labels = torch.randint(0, O, (N, H, W), device=dev, generator=g)
+    labels[torch.rand((N, H, W), device=dev, generator=g) > 0.05] = 255
+    lab8 = labels.to(torch.uint8)
+
+    def ours():
+        x = logits.detach().requires_grad_(True)
+        loss, _, _ = fused_seg_loss(x, lab8, (H, W), 1.0)
+        loss.backward()
+        return loss, x.grad
+
+    def torch_seq():
+        x = logits.detach().requires_grad_(True)
+        out = F.interpolate(x, size=(H, W), mode="bilinear", align_corners=True)
+        p = torch.softmax(out, dim=1)
+        m = (p < 0.05).detach()
+        loss = F.cross_entropy(out, labels, ignore_index=255) + torch.sum(-1 * m * torch.log(1 - p + 1e-6)) / torch.sum(m)
+        loss.backward()
+        return loss, x.grad
+
+    res = {}
+    vals = {}
+    for name, fn in (("halo_seg_loss", ours), ("torch_eager_sequence", torch_seq)):
+        for _ in range(2):
+            vals[name] = fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name + "_ms"] = round(e0.elapsed_time(e1) / 5, 3)
+    a, b = vals["halo_seg_loss"], vals["torch_eager_sequence"]
+    res["loss_rel_diff"] = abs(float(a[0]) - float(b[0])) / abs(float(b[0]))
+    res["grad_rel_diff_of_max"] = float((a[1] - b[1]).abs().max() / b[1].abs().max())
+    res["workload"] = "fwd+bwd of CE(ignore 255) + negative-learning loss on logits %dx%dx%dx%d up-sampled to %dx%d" % (N, O, h, w, H, W)
+    return res
 
 
 class _Features(dict):

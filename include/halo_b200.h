@@ -211,6 +211,23 @@ int halo_round_delta_apply(uint8_t* masks, const int* row_image, const int* pick
                            const uint8_t* lab, int rows, int cap, int H, int W, int active_radius, halo_stream_t stream);
 
 
+/* ---- losses on the head's logits, fused with the up-sampling in front of them and its adjoint -------
+ * Replaces, in the training step (core/train_learners.py:343-356 target branch, :232-236 source branch):
+ *     out = F.interpolate(logits_lr, (H,W), bilinear, align_corners=True)        core/models/classifier.py:556-557
+ *     loss_sup = CrossEntropyLoss(ignore_index=255)(out, labels)                  skipped when no pixel is labelled
+ *     negative = NegativeLearningLoss(threshold)(softmax(out)) * neg_weight       core/loss/negative_learning_loss.py:6-16
+ *     (loss_sup + negative).backward()  down to logits_lr
+ * without materialising `out`, its softmax or their gradients.
+ *   logits_lr [N,O,h,w] f32;  labels [N,H,W] u8 (255 = ignore) | NULL (no supervised term);  neg_weight = SOLVER.NEGATIVE_LOSS
+ *   (0 disables the negative term);  threshold = 0.05 in the reference.
+ *   losses [4] f32 out = {loss_sup + negative, loss_sup, negative (weighted), number of labelled pixels}
+ *   dlogits_lr [N,O,h,w] f32 out | NULL = d(loss_sup + negative)/d logits_lr.  Deterministic (gather, fixed-order sums).
+ *   ws: halo_seg_loss_workspace_bytes() bytes. */
+size_t halo_seg_loss_workspace_bytes(void);
+int halo_seg_loss(const float* logits_lr, const uint8_t* labels, float neg_weight, float threshold, float* losses,
+                  float* dlogits_lr, int N, int O, int h, int w, int H, int W, void* ws, size_t ws_bytes,
+                  halo_stream_t stream);
+
 /* ---- packed round rows: the ONE exchange at the end of a sharded round (the reference runs the round on
  * rank 0 alone, core/train_learners.py:307-326, so this has no reference counterpart beyond build.py:58-62) ------------
  * One row per pool image, row_bytes = halo_round_row_bytes(cap, a) (a multiple of 16):
