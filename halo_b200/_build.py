@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhalo_sm100.so")
-SOURCES = ["abi.cu", "head_fwd.cu", "head_fwd_tc.cu", "head_misc.cu", "head_bwd.cu", "head_bwd_tc.cu", "head_bwd_dw_tc.cu", "head_bwd_stream_tc.cu", "score.cu", "upsample.cu", "select.cu", "delta.cu", "seg_loss.cu"]
+SOURCES = ["abi.cu", "head_fwd.cu", "head_fwd_tc.cu", "head_misc.cu", "head_bwd.cu", "head_bwd_tc.cu", "head_bwd_dw_tc.cu", "head_bwd_stream_tc.cu", "score.cu", "upsample.cu", "select.cu", "delta.cu", "seg_loss.cu", "reduce_hfr.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

@@ -59,6 +59,8 @@ _SIGNATURES = {
     "halo_round_rows_pack": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "halo_round_rows_apply": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "halo_checksum64": (_i, [_vp, _sz, ctypes.c_ulonglong, _vp, _i, _vp]),
+    "halo_reduce_hfr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "halo_reduce_hfr_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "halo_seg_loss_workspace_bytes": (_sz, []),
     "halo_seg_loss": (_i, [_vp, _vp, _f, _f, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
 }

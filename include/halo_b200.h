@@ -211,6 +211,22 @@ int halo_round_delta_apply(uint8_t* masks, const int* row_image, const int* pick
                            const uint8_t* lab, int rows, int cap, int H, int W, int active_radius, halo_stream_t stream);
 
 
+/* ---- channel reduction + hyperbolic feature re-weighting upstream of the head, evaluation mode --------
+ * Replaces core/models/classifier.py:526-550 (and the same block of the v2 head, :187-214) as the acquisition round runs
+ * them (classifier.eval(), core/active/build.py:72-73):
+ *     y = conv_reduce(f)                                   1x1 conv Cin -> C with bias
+ *     wt = clamp(mean_pixels(wn_mlp(y)), 1e-5)             Linear, BatchNorm1d (running statistics), ReLU, Linear
+ *     z = F.normalize(y over the pixels of each channel) * wt
+ *   feat [N,Cin,H,W] f32; Wr [C,Cin], br [C]|NULL (conv_reduce.weight / .bias);
+ *   W1 [C,C], b1 [C], bn_gamma/beta/mean/var [C], bn_eps, W2 [C,C], b2 [C] (wn_mlp[0], [1], [3]); W1 = NULL: no HFR (z = y)
+ *   out [N,C,H,W] f32 = z, the features HyperMapper.expmap / halo_head_fwd read next; scale_out [N,C] f32 | NULL = z / y
+ * HFR needs C <= 128.  Forward only: a classifier in training mode (batch statistics, autograd) keeps its torch modules. */
+size_t halo_reduce_hfr_workspace_bytes(int N, int C, int H, int W);
+int halo_reduce_hfr_fwd(const float* feat, const float* Wr, const float* br, const float* W1, const float* b1,
+                        const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var,
+                        float bn_eps, const float* W2, const float* b2, float* out, float* scale_out,
+                        int N, int Cin, int C, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
+
 /* ---- losses on the head's logits, fused with the up-sampling in front of them and its adjoint -------
  * Replaces, in the training step (core/train_learners.py:343-356 target branch, :232-236 source branch):
  *     out = F.interpolate(logits_lr, (H,W), bilinear, align_corners=True)        core/models/classifier.py:556-557
