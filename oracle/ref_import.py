@@ -122,6 +122,28 @@ def load():
     return ns
 
 
+def load_training_side():
+    """The reference's classifier module and negative-learning loss, for the rows next to the hot path (SURVEY 8f rows 3,
+    4).  core/models/__init__.py pulls mmcv in through resnet.py, so classifier.py is loaded on its own; it only needs torch
+    and core.utils.hyperbolic (already stubbed by `load`)."""
+    import importlib.util
+
+    load()
+    with cpu_only():
+        if "core.models.classifier" not in sys.modules:
+            if "core.models" not in sys.modules:
+                pkg = types.ModuleType("core.models")
+                pkg.__path__ = [os.path.join(REFERENCE_ROOT, "core", "models")]
+                sys.modules["core.models"] = pkg
+            spec = importlib.util.spec_from_file_location("core.models.classifier",
+                                                          os.path.join(REFERENCE_ROOT, "core", "models", "classifier.py"))
+            m = importlib.util.module_from_spec(spec)
+            sys.modules["core.models.classifier"] = m
+            spec.loader.exec_module(m)
+        from core.loss.negative_learning_loss import NegativeLearningLoss  # noqa
+    return types.SimpleNamespace(classifier=sys.modules["core.models.classifier"], NegativeLearningLoss=NegativeLearningLoss)
+
+
 @contextlib.contextmanager
 def cpu_only():
     """Run reference code on a CUDA-less host: `.cuda()` becomes the identity."""

@@ -33,4 +33,4 @@ def pytest_collection_modifyitems(config, items):
 def golden():
     import numpy as np
 
-    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("head", "score", "select")}
+    return {name: np.load(os.path.join(GOLDEN, name + ".npz")) for name in ("head", "score", "select", "train")}

@@ -164,8 +164,86 @@ def select_fixtures(ref):
     return out
 
 
+def train_fixtures():
+    """Rows next to the hot path, from the reference's own classes:
+    * `DepthwiseSeparableASPP_Hyper` (core/models/classifier.py:388-558) built small, in eval mode, run end to end on the
+      CPU: the input of its conv_reduce (captured by a hook), the parameters of conv_reduce / wn_mlp / conv_seg, and what
+      its forward returns (logits, float64 embedding) -- pins conv_reduce + HFR (:526-550) and the head call site (:552-554)
+      under the reference's real classifier class;
+    * the learner's loss sequence (core/train_learners.py:343-356) with the reference's NegativeLearningLoss
+      (core/loss/negative_learning_loss.py) in float64, and its gradient w.r.t. the low-resolution logits."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    side = ref_import.load_training_side()
+    out = {}
+    torch.manual_seed(11)
+    C, O = 32, 19
+    with ref_import.cpu_only():
+        clf = side.classifier.DepthwiseSeparableASPP_Hyper(inplanes=48, dilation_series=[1, 2], padding_series=[1, 2],
+                                                           num_classes=O, norm_layer=nn.BatchNorm2d, reduced_channels=C, hfr=True)
+    with torch.no_grad():   # statistics / parameters as after some training, not the initial identity
+        for mod in clf.modules():
+            if isinstance(mod, (nn.BatchNorm1d, nn.BatchNorm2d)):
+                mod.running_mean.uniform_(-0.2, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.uniform_(-0.2, 0.2)
+    clf.eval()
+    captured = {}
+    clf.conv_reduce.register_forward_hook(lambda m, i, o: captured.update(f=i[0].detach().clone()))
+    x = {"out": torch.randn(2, 48, 9, 12), "low": torch.randn(2, 256, 18, 24)}
+    with torch.no_grad(), ref_import.cpu_only():
+        logits, emb = clf(x, size=None)
+    out["hfr_f"] = captured["f"].numpy()
+    out["hfr_Wr"] = clf.conv_reduce.weight.detach().numpy()
+    out["hfr_br"] = clf.conv_reduce.bias.detach().numpy()
+    lin1, bn, lin2 = clf.wn_mlp[0], clf.wn_mlp[1], clf.wn_mlp[3]
+    for name, t_ in (("W1", lin1.weight), ("b1", lin1.bias), ("bn_w", bn.weight), ("bn_b", bn.bias), ("bn_mean", bn.running_mean),
+                     ("bn_var", bn.running_var), ("W2", lin2.weight), ("b2", lin2.bias), ("P", clf.conv_seg.P_MLR),
+                     ("A", clf.conv_seg.A_MLR)):
+        out["hfr_" + name] = t_.detach().numpy()
+    out["hfr_bn_eps"] = np.float64(bn.eps)
+    out["hfr_c"] = np.float64(clf.conv_seg.c)
+    out["hfr_logits"] = logits.numpy()
+    out["hfr_emb"] = emb.numpy()
+    # loss sequence
+    neg_crit = side.NegativeLearningLoss(threshold=0.05)
+    g = torch.Generator().manual_seed(12)
+    for i, (N, h, w, H, W, wgt, lab_frac) in enumerate(((2, 10, 14, 37, 50, 1.0, 0.3), (1, 8, 8, 8, 8, 0.5, 1.0), (1, 6, 9, 24, 33, 1.0, 0.0))):
+        lg = (torch.randn((N, O, h, w), generator=g) * 3.0).double().requires_grad_(True)
+        lab = torch.randint(0, O, (N, H, W), generator=g)
+        lab[torch.rand((N, H, W), generator=g) >= lab_frac] = 255
+        tgt_out = F.interpolate(lg, size=(H, W), mode="bilinear", align_corners=True)      # classifier.py:556-557
+        predict = torch.softmax(tgt_out, dim=1)                                            # train_learners.py:343
+        loss = torch.zeros((), dtype=torch.float64)
+        sup = torch.zeros((), dtype=torch.float64)
+        if torch.sum(lab != 255) != 0:                                                     # :346
+            sup = nn.CrossEntropyLoss(ignore_index=255)(tgt_out, lab)
+            loss = loss + sup
+        neg = neg_crit(predict) * wgt                                                      # :351-353
+        loss = loss + neg
+        loss.backward()
+        tag = "loss%d_" % i
+        out[tag + "logits"] = lg.detach().numpy()
+        out[tag + "labels"] = lab.numpy().astype(np.uint8)
+        out[tag + "size"] = np.array([H, W], dtype=np.int64)
+        out[tag + "weight"] = np.float64(wgt)
+        out[tag + "loss"] = loss.detach().numpy()
+        out[tag + "sup"] = sup.detach().numpy()
+        out[tag + "neg"] = neg.detach().numpy()
+        out[tag + "grad"] = lg.grad.numpy()
+    out["n_loss_cases"] = np.int64(3)
+    return out
+
+
 def main():
     ref = ref_import.load()
+    if "--train-only" in sys.argv:
+        np.savez_compressed(os.path.join(HERE, "train.npz"), **train_fixtures())
+        print("train.npz", os.path.getsize(os.path.join(HERE, "train.npz")) // 1024, "KiB")
+        return
+    np.savez_compressed(os.path.join(HERE, "train.npz"), **train_fixtures())
     np.savez_compressed(os.path.join(HERE, "head.npz"), **head_fixtures(ref))
     np.savez_compressed(os.path.join(HERE, "score.npz"), **score_fixtures(ref))
     np.savez_compressed(os.path.join(HERE, "select.npz"), **select_fixtures(ref))

@@ -53,3 +53,23 @@ def test_reduce_hfr_feeds_the_fused_head_and_refuses_training_mode():
     with pytest.raises(RuntimeError, match="no CPU path"):
         wn_mlp.eval()
         reduce_hfr(f, conv_reduce, wn_mlp)
+
+
+def test_reference_classifier_golden(golden):
+    """conv_reduce + HFR + fused head on the GPU against what the reference's real classifier class
+    (DepthwiseSeparableASPP_Hyper, core/models/classifier.py:526-558) returned for the same decoder features: its float64
+    embedding and its logits (tests/golden/train.npz, frozen from the live reference)."""
+    from tests.test_oracle_golden import _hfr_modules, t
+
+    g = golden["train"]
+    conv, mlp = _hfr_modules(g, torch.float32)
+    c = float(g["hfr_c"])
+    with torch.no_grad():
+        z = reduce_hfr(t(g["hfr_f"]).to(DEV), conv, mlp)
+        mapper = halo_b200.HyperMapper(c=c)
+        mlr = halo_b200.HyperMLR(z.shape[1], 19, c=c).to(DEV)
+        mlr.load_state_dict({"P_MLR": t(g["hfr_P"]), "A_MLR": t(g["hfr_A"])})
+        emb = mapper.expmap(z, dim=1)                    # classifier.py:553
+        out = mlr(emb.double()).float()                  # classifier.py:554
+    assert rel_err(out, t(g["hfr_logits"])) <= 2 * TOL
+    assert rel_err(emb.materialize(), t(g["hfr_emb"])) <= 2 * TOL

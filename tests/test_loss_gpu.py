@@ -95,3 +95,20 @@ def test_fused_loss_behind_the_fused_head():
     assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
     assert rel_err(u1.grad, u0.grad) <= 1e-4
     assert rel_err(mlr.P_MLR.grad, P0.grad) <= 1e-4 and rel_err(mlr.A_MLR.grad, A0.grad) <= 1e-4
+
+
+def test_fused_loss_matches_golden(golden):
+    """Against the learner's sequence run with the reference's own NegativeLearningLoss (tests/golden/train.npz)."""
+    from tests.util import t
+
+    g = golden["train"]
+    for i in range(int(g["n_loss_cases"])):
+        tag = "loss%d_" % i
+        size = tuple(int(v) for v in g[tag + "size"])
+        x = t(g[tag + "logits"]).float().to(DEV).requires_grad_(True)
+        loss, sup, neg = fused_seg_loss(x, t(g[tag + "labels"]).to(DEV), size, neg_weight=float(g[tag + "weight"]))
+        loss.backward()
+        assert abs(float(loss) - float(g[tag + "loss"])) <= 1e-5 * max(1.0, abs(float(g[tag + "loss"])))
+        assert abs(float(sup) - float(g[tag + "sup"])) <= 1e-5 * max(1.0, abs(float(g[tag + "sup"])))
+        assert abs(float(neg) - float(g[tag + "neg"])) <= 1e-5 * max(1.0, abs(float(g[tag + "neg"])))
+        assert rel_err(x.grad, t(g[tag + "grad"])) <= 1e-5

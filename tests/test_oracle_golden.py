@@ -110,3 +110,50 @@ def test_oracle_vs_live_reference():
                     ground_truth=gt, in_channels=O, size=size, ctor_purity_type=ctor, K=100, c=c)
                 assert s.dtype == s_ref.dtype
                 assert torch.nan_to_num(s - s_ref).abs().max().item() <= 1e-6 * max(torch.nan_to_num(s_ref).abs().max().item(), 1e-30)
+
+
+def _hfr_modules(g, dtype=torch.float64):
+    """conv_reduce / wn_mlp rebuilt from the golden parameters of the reference's own classifier instance."""
+    import torch.nn as nn
+
+    Wr = t(g["hfr_Wr"])
+    C, Cin = Wr.shape[0], Wr.shape[1]
+    conv = nn.Conv2d(Cin, C, kernel_size=1)
+    mlp = nn.Sequential(nn.Linear(C, C), nn.BatchNorm1d(C, eps=float(g["hfr_bn_eps"])), nn.ReLU(), nn.Linear(C, C))
+    with torch.no_grad():
+        conv.weight.copy_(Wr); conv.bias.copy_(t(g["hfr_br"]))
+        mlp[0].weight.copy_(t(g["hfr_W1"])); mlp[0].bias.copy_(t(g["hfr_b1"]))
+        mlp[1].weight.copy_(t(g["hfr_bn_w"])); mlp[1].bias.copy_(t(g["hfr_bn_b"]))
+        mlp[1].running_mean.copy_(t(g["hfr_bn_mean"])); mlp[1].running_var.copy_(t(g["hfr_bn_var"]))
+        mlp[3].weight.copy_(t(g["hfr_W2"])); mlp[3].bias.copy_(t(g["hfr_b2"]))
+    return conv.to(dtype).eval(), mlp.to(dtype).eval()
+
+
+def test_hfr_and_head_call_site_match_the_reference_classifier(golden):
+    """oracle/hfr.py + oracle/head.py against what the reference's REAL classifier class returned
+    (DepthwiseSeparableASPP_Hyper.forward, core/models/classifier.py:526-558, frozen by tests/golden/make_golden.py)."""
+    from oracle import hfr as ohfr
+
+    g = golden["train"]
+    conv, mlp = _hfr_modules(g, torch.float32)      # the reference runs this block in float32
+    with torch.no_grad():
+        z = ohfr.reduce_hfr(t(g["hfr_f"]), conv, mlp)
+    logits, x, _ = ohead.head_forward(z, t(g["hfr_P"]), t(g["hfr_A"]), float(g["hfr_c"]))
+    assert torch.equal(x, t(g["hfr_emb"]))
+    ref = t(g["hfr_logits"])
+    assert (logits - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+
+
+def test_loss_oracle_matches_the_reference_sequence(golden):
+    """oracle/loss.py against the learner's sequence run with the reference's own NegativeLearningLoss class."""
+    from oracle import loss as oloss
+
+    g = golden["train"]
+    for i in range(int(g["n_loss_cases"])):
+        tag = "loss%d_" % i
+        size = tuple(int(v) for v in g[tag + "size"])
+        loss, sup, neg, grad = oloss.seg_loss(t(g[tag + "logits"]), t(g[tag + "labels"]).long(), size, neg_weight=float(g[tag + "weight"]))
+        assert abs(float(loss) - float(g[tag + "loss"])) <= 1e-12 * max(1.0, abs(float(g[tag + "loss"])))
+        assert abs(float(sup) - float(g[tag + "sup"])) <= 1e-12 and abs(float(neg) - float(g[tag + "neg"])) <= 1e-12
+        ref = t(g[tag + "grad"])
+        assert (grad - ref).abs().max().item() <= 1e-12 * ref.abs().max().item()
