@@ -160,7 +160,7 @@ class RoundExchange:
     `pack_fn` / `apply_fn` default to the CUDA entry points; the world_size-2 gloo tests (no GPU) pass the oracle's
     restatement to exercise the sharding and the collective on CPU tensors."""
 
-    def __init__(self, n_images, H, W, cap, active_radius, device, *, group=None, pack_fn=None, apply_fn=None):
+    def __init__(self, n_images, H, W, cap, active_radius, device, *, group=None, pack_fn=None, apply_fn=None, depth=2):
         import torch.distributed as dist
 
         self.group = group
@@ -174,40 +174,63 @@ class RoundExchange:
         k2 = (2 * self.r + 1) ** 2
         self.row_bytes = (4 + 4 * self.cap + self.cap * k2 + 15) // 16 * 16
         self.pack_fn, self.apply_fn = pack_fn or pack_rows, apply_fn or apply_rows
-        # zeroed once: padding rows keep count = 0 for ever, real rows are rewritten by every round's pack
-        self.rows_local = torch.zeros((self.per, self.row_bytes), dtype=torch.uint8, device=self.device)
-        self.rows_all = (torch.empty((self.world * self.per, self.row_bytes), dtype=torch.uint8, device=self.device)
-                         if self.distributed else self.rows_local)
+        # `depth` send buffers used round-robin, so that the next round can be packed while the previous round's all-gather
+        # is still reading its buffer (back-to-back rounds never wait for the slowest rank of the last one).  Zeroed once:
+        # padding rows keep count = 0 for ever, real rows are rewritten by every round's pack.
+        self.depth = max(1, int(depth))
+        self._rows = [torch.zeros((self.per, self.row_bytes), dtype=torch.uint8, device=self.device) for _ in range(self.depth)]
+        self._all = [(torch.empty((self.world * self.per, self.row_bytes), dtype=torch.uint8, device=self.device)
+                      if self.distributed else self._rows[k]) for k in range(self.depth)]
         self.row_image = _row_maps(self.n_images, self.world, self.device)[0]
         self.cuda = self.device.type == "cuda"
         self.side = torch.cuda.Stream(device=self.device) if self.cuda else None
-        self.done = torch.cuda.Event() if self.cuda else None
+        self._done = [torch.cuda.Event() if self.cuda else None for _ in range(self.depth)]
+        self._used = [False] * self.depth
+        self._cur = 0           # buffer the current round packs into
+        self._last = None       # buffer of the last exchange issued (what wait() joins)
+        self._fresh = True      # nothing packed into the current buffer yet this round
+
+    @property
+    def rows_local(self):
+        return self._rows[self._cur]
 
     def pack(self, local_row, picks, n_picked, gt):
         """Rows [local_row, local_row + b) of this shard <- the picks of a batch of b images (caller's stream)."""
         b = picks.shape[0]
-        self.pack_fn(self.rows_local[local_row:local_row + b], picks, n_picked, gt, self.cap, self.r)
+        if self._fresh and self.cuda and self._used[self._cur]:
+            # first pack of a round into a buffer an earlier exchange sent from: that exchange must have finished with it
+            torch.cuda.current_stream(self.device).wait_event(self._done[self._cur])
+        self._fresh = False
+        self.pack_fn(self._rows[self._cur][local_row:local_row + b], picks, n_picked, gt, self.cap, self.r)
 
     def exchange(self, masks, n_picked_out):
         """All-gather the shard rows (one collective) and replay every rank's rows onto `masks` / `n_picked_out`."""
         import torch.distributed as dist
 
+        k = self._cur
+        rows, rows_all = self._rows[k], self._all[k]
+
         def run():
             if self.distributed:
-                dist.all_gather_into_tensor(self.rows_all, self.rows_local, group=self.group)
-            self.apply_fn(masks, self.row_image, self.rows_all, n_picked_out, self.cap, self.r)
+                dist.all_gather_into_tensor(rows_all, rows, group=self.group)
+            self.apply_fn(masks, self.row_image, rows_all, n_picked_out, self.cap, self.r)
 
         if self.cuda:
             self.side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self.side):
                 run()
-                self.done.record(self.side)
+                self._done[k].record(self.side)
         else:
             run()
+        self._used[k] = True
+        self._last = k
+        self._cur = (k + 1) % self.depth
+        self._fresh = True
 
     def wait(self):
-        if self.cuda:
-            torch.cuda.current_stream(self.device).wait_event(self.done)
+        """The caller's stream waits for the last exchange issued (masks / counts are then complete on it)."""
+        if self.cuda and self._last is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._done[self._last])
 
     def bytes_per_rank(self):
         return self.per * self.row_bytes
