@@ -150,6 +150,75 @@ __device__ __forceinline__ float mlr_logit(float S, float T, const PixelScalars&
   return hc.two_over_s * an * fast_asinh(arg);                            // :181-183 (lambda_term = 2.0)
 }
 
+// ---- the same epilogue for TWO classes at a time on the packed fp32x2 pipe (sm_100: FFMA2 / FADD2 / FMUL2) ------------
+// Every multiply / add of mlr_logit above becomes one packed instruction for the class pair; comparisons, selects, min /
+// max and the MUFU calls stay scalar per half.  Same operations in the same order per component, so each half is
+// bit-identical to mlr_logit.  The epilogue warpgroup is K1's critical role (profiles/r2_k1.md): ~45 -> ~25 issue slots
+// per class.
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 mlr_logit2(float2 S, float2 T, const PixelScalars& ps, float2 pp, float2 an, float2 pa,
+                                             float2 Bk, const HeadConsts& hc) {
+  const float2 g2 = f2(ps.gamma);
+  const float2 px = __fmul2_rn(g2, S);
+  const float2 xa = __fmul2_rn(g2, T);
+  const float2 cpx2 = __fmul2_rn(f2(2.f * hc.c), px);
+  const float2 Anum = __fadd2_rn(__fadd2_rn(f2(1.f), cpx2), f2(ps.t2));                      // :150
+  float2 D = __ffma2_rn(f2(hc.c * ps.t2), pp, __fadd2_rn(f2(1.f), cpx2));                   // :152-153
+  D.x = fmaxf(D.x, 1e-12f); D.y = fmaxf(D.y, 1e-12f);
+  const float2 num = __ffma2_rn(Bk, xa, __fmul2_rn(Anum, pa));                              // :175-177
+  const float2 bo = __fmul2_rn(Bk, f2(ps.omega));
+  const float2 thr = __fmul2_rn(f2(hc.om_max), D);
+  const bool in0 = bo.x >= thr.x, in1 = bo.y >= thr.y;
+  const float2 dlo = __fmul2_rn(f2(1e-12f), D);
+  const float2 den = make_float2(fmaxf(bo.x, dlo.x), fmaxf(bo.y, dlo.y));
+  float2 dmb = __fadd2_rn(D, make_float2(-bo.x, -bo.y));
+  dmb.x = fmaxf(dmb.x, 0.f); dmb.y = fmaxf(dmb.y, 0.f);
+  const float2 xo_a = __fmul2_rn(__fmul2_rn(D, dmb), f2(hc.inv_c));
+  const float2 xo_b = __fmul2_rn(__fmul2_rn(D, D), f2(1e-24f));
+  const float2 dd = __fmul2_rn(den, den);
+  const float x2a = in0 ? dd.x : fmaxf(xo_a.x, xo_b.x);
+  const float x2b = in1 ? dd.y : fmaxf(xo_a.y, xo_b.y);
+  const float2 kk = make_float2(in0 ? hc.two_s : hc.out_scale, in1 ? hc.two_s : hc.out_scale);
+  const float2 rs = make_float2(fast_rsqrt(fmaxf(x2a, 1e-36f)), fast_rsqrt(fmaxf(x2b, 1e-36f)));
+  const float2 arg = __fmul2_rn(__fmul2_rn(num, kk), rs);
+  // asinh, two at a time
+  const float2 ax = make_float2(fabsf(arg.x), fabsf(arg.y));
+  const float2 v = __ffma2_rn(ax, ax, f2(1.f));
+  const float2 vr = make_float2(fast_rsqrt(v.x), fast_rsqrt(v.y));
+  const float2 tm = __ffma2_rn(v, vr, ax);                                                   // ax + v * rsqrt(v)
+  const float ta = (ax.x > 1e9f) ? 2.f * ax.x : tm.x, tb = (ax.y > 1e9f) ? 2.f * ax.y : tm.y;
+  const float2 ln = __fmul2_rn(make_float2(fast_lg2(ta), fast_lg2(tb)), f2(0.69314718056f));
+  const float2 ash = make_float2(copysignf(ln.x, arg.x), copysignf(ln.y, arg.y));
+  return __fmul2_rn(__fmul2_rn(f2(hc.two_over_s), an), ash);                                 // :181-183
+}
+
+// entropy-only softmax over OP/2 class pairs (the packed twin of softmax_entropy_only below)
+template <int OP>
+__device__ __forceinline__ float softmax_entropy_only2(const float2 (&l)[OP / 2], const HeadConsts& hc) {
+  float mx = fmaxf(l[0].x, l[0].y);
+#pragma unroll
+  for (int j = 1; j < OP / 2; ++j) mx = fmaxf(mx, fmaxf(l[j].x, l[j].y));
+  float2 e[OP / 2];
+  float2 Z = f2(0.f);
+  const float2 nmx = f2(-mx);
+#pragma unroll
+  for (int j = 0; j < OP / 2; ++j) {
+    const float2 d = __fmul2_rn(__fadd2_rn(l[j], nmx), f2(1.44269504089f));
+    e[j] = make_float2(fast_ex2(d.x), fast_ex2(d.y));
+    Z = __fadd2_rn(Z, e[j]);
+  }
+  const float2 iz = f2(fast_rcp(Z.x + Z.y));
+  float2 ent = f2(0.f);
+#pragma unroll
+  for (int j = 0; j < OP / 2; ++j) {
+    const float2 p = __fmul2_rn(e[j], iz);
+    const float2 q = __fadd2_rn(p, f2(1e-6f));
+    const float2 lg = make_float2(fast_lg2(q.x), fast_lg2(q.y));
+    ent = __ffma2_rn(make_float2(-p.x, -p.y), lg, ent);
+  }
+  return (ent.x + ent.y) * (0.69314718056f * hc.inv_log19);
+}
+
 // softmax entropy (floating_region.py:72-76) / 1-p[gt] (:77-83) and arg-max (:166) from logits in registers
 template <int OP>
 __device__ __forceinline__ void softmax_stats(const float (&l)[OP], int O, const HeadConsts& hc, int pixunc_mode,

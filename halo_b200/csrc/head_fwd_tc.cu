@@ -116,8 +116,12 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     const float4* src = reinterpret_cast<const float4*>(wtc);
     float4* dst = reinterpret_cast<float4*>(sW);
     for (int i = threadIdx.x; i < n4; i += TC_THREADS) dst[i] = src[i];
-    const float* csrc = wtc + (size_t)2 * NR * C;  // [4][OP] -> per-class float4 {pp, an, pa, Bk}
-    for (int i = threadIdx.x; i < 4 * OP; i += TC_THREADS) sCls[(i % OP) * 4 + i / OP] = csrc[i];
+    // [4][OP] -> per class PAIR two float4 {pp0, pp1, an0, an1} {pa0, pa1, Bk0, Bk1} (operands of the packed epilogue)
+    const float* csrc = wtc + (size_t)2 * NR * C;
+    for (int i = threadIdx.x; i < 4 * OP; i += TC_THREADS) {
+      const int q = i / OP, k = i % OP;
+      sCls[(k >> 1) * 8 + q * 2 + (k & 1)] = csrc[i];
+    }
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -278,9 +282,10 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       mbar_wait(&acc_full[g], (uint32_t)it & 1u);
       tc_fence_after();
       const float n2 = sN2[g * TC_BM + m];
-      float S[OP], T[OP];
+      // the contractions as class PAIRS (float2 = one 64-bit register pair = one operand of FFMA2 / FADD2 / FMUL2)
+      float2 S2[OP / 2], T2[OP / 2];
 #pragma unroll
-      for (int k = 0; k < OP; ++k) S[k] = T[k] = 0.f;
+      for (int j = 0; j < OP / 2; ++j) S2[j] = T2[j] = make_float2(0.f, 0.f);
       static_assert((2 * OP) % 8 == 0, "OP is a multiple of 4");
 #pragma unroll
       for (int qa = 0; qa < NACC; ++qa) {
@@ -291,9 +296,9 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
           for (int c8 = 0; c8 < (2 * OP) / 8; ++c8) tmem_ld_x8(taddr + c8 * 8, *reinterpret_cast<float(*)[8]>(&buf[c8 * 8]));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int col = 0; col < 2 * OP; ++col) {
-            if (col < OP) S[col] += buf[col];
-            else T[col - OP] += buf[col];
+          for (int j = 0; j < OP / 2; ++j) {
+            S2[j] = __fadd2_rn(S2[j], make_float2(buf[2 * j], buf[2 * j + 1]));
+            T2[j] = __fadd2_rn(T2[j], make_float2(buf[OP + 2 * j], buf[OP + 2 * j + 1]));
           }
         }
       }
@@ -307,10 +312,14 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
         // the features ONCE (164 B per pixel saved here against a second 4*C-byte pass over u there)
         float* sv = a.saved + (size_t)n * (2 * OP + 1) * HW + p;
 #pragma unroll
-        for (int k = 0; k < OP; ++k) {
-          if (k < a.O) {
-            __stcs(sv + (size_t)k * HW, S[k]);
-            __stcs(sv + (size_t)(OP + k) * HW, T[k]);
+        for (int j = 0; j < OP / 2; ++j) {
+          if (2 * j < a.O) {
+            __stcs(sv + (size_t)(2 * j) * HW, S2[j].x);
+            __stcs(sv + (size_t)(OP + 2 * j) * HW, T2[j].x);
+          }
+          if (2 * j + 1 < a.O) {
+            __stcs(sv + (size_t)(2 * j + 1) * HW, S2[j].y);
+            __stcs(sv + (size_t)(OP + 2 * j + 1) * HW, T2[j].y);
           }
         }
         __stcs(sv + (size_t)(2 * OP) * HW, n2);
@@ -318,19 +327,24 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       if (a.logits == nullptr && a.radius == nullptr && a.pixunc == nullptr && a.label == nullptr && a.stats == nullptr)
         continue;   // contraction-only launch (backward called without saved planes)
       const PixelScalars ps = tangent_scalars(n2, hc);
-      float l[OP];
+      float2 l2[OP / 2];
 #pragma unroll
-      for (int k = 0; k < OP; ++k) {
-        l[k] = -3.0e38f;     // padded classes: skipped (warp-uniform), and invisible to the softmax below
-        if (k < OP - 3 || k < a.O) {
-          const float4 cl = reinterpret_cast<const float4*>(sCls)[k];
-          l[k] = mlr_logit(S[k], T[k], ps, cl.x, cl.y, cl.z, cl.w, hc);
+      for (int j = 0; j < OP / 2; ++j) {
+        l2[j] = make_float2(-3.0e38f, -3.0e38f);   // padded classes: skipped (warp-uniform), invisible to the softmax below
+        if (2 * j < OP - 3 || 2 * j < a.O) {
+          const float4 c0 = reinterpret_cast<const float4*>(sCls)[2 * j], c1 = reinterpret_cast<const float4*>(sCls)[2 * j + 1];
+          l2[j] = mlr_logit2(S2[j], T2[j], ps, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y),
+                             make_float2(c1.z, c1.w), hc);
+          if (2 * j + 1 >= a.O) l2[j].y = -3.0e38f;   // the odd half of the last pair when O is odd
         }
       }
+      float l[OP];
+#pragma unroll
+      for (int j = 0; j < OP / 2; ++j) { l[2 * j] = l2[j].x; l[2 * j + 1] = l2[j].y; }
 #ifdef HALO_TC_VARIANTS
       if (a.debug_raw) {  // numerics probe: expose the raw contractions <u,a_hat_k> instead of the logits
 #pragma unroll
-        for (int k = 0; k < OP; ++k) l[k] = T[k];
+        for (int j = 0; j < OP / 2; ++j) { l[2 * j] = T2[j].x; l[2 * j + 1] = T2[j].y; }
       }
 #endif
       const float r = (a.norm_mode == HALO_NORM_EUCLID) ? ps.xnorm : ps.radius;
@@ -348,7 +362,7 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
         if (a.gt != nullptr && live) gtv = a.gt[pix];
         float unc;
         int lab = 0;
-        if (a.label == nullptr && a.pixunc_mode == HALO_PIXUNC_ENTROPY) unc = softmax_entropy_only<OP>(l, hc);
+        if (a.label == nullptr && a.pixunc_mode == HALO_PIXUNC_ENTROPY) unc = softmax_entropy_only2<OP>(l2, hc);
         else softmax_stats<OP>(l, a.O, hc, a.pixunc_mode, a.label_mode, gtv, unc, lab);
         if (live) {
           if (a.pixunc != nullptr) __stcs(a.pixunc + pix, unc);
