@@ -14,8 +14,7 @@
 // One persistent 512-thread CTA per SM, per 128-pixel tile i:
 //   warps 8-11 / 12-15  two DERIVATIVE warpgroups on alternate tiles (thread = pixel = TMEM lane): saved S, T, |u|^2 and
 //                 dlogits -> gS, gT (kept in registers), alpha, class-scalar partials; once the previous tile has released
-//                 the G buffers: G as TF32 hi/lo into TMEM (A operand of the du GEMM -- early, so that the first du GEMM of
-//                 the tile overlaps the previous tile's stream) and, pixel chunk by pixel chunk, into shared memory in the
+//                 the G buffers: G as TF32 hi/lo into TMEM (A operand of the du GEMM) and into shared memory in the
 //                 K-major SWIZZLE_128B layout [n][px] (B operand of the dW GEMM).  The same warpgroup then runs the OUTPUT
 //                 pass of its tile: warp q takes the stages of pixel chunk q -- D2 from TMEM (its own lanes) + alpha*u with
 //                 u read from the stage in shared memory -> coalesced 128-byte du stores.
@@ -75,7 +74,7 @@ __host__ __device__ inline BsSmem bs_smem_layout(int NP, int OP, int C) {
   int st = (budget > L.ring_off + tail) ? (int)((budget - L.ring_off - tail) / BS_STAGE_BYTES) : 0;
   L.stages = st > BS_MAX_STAGES ? BS_MAX_STAGES : st;
   L.bar_off = L.ring_off + (size_t)L.stages * BS_STAGE_BYTES;
-  const int nbars = 2 * BS_MAX_STAGES + 2 + 2 * BS_NQ + 4 + 4 + 2;
+  const int nbars = 2 * BS_MAX_STAGES + 3 + 4 + 4 + 2;
   L.tmem_off = L.bar_off + (size_t)nbars * 8;
   L.cls_off = (L.tmem_off + 16 + 15) / 16 * 16;
   L.red_off = L.cls_off + (size_t)4 * OP * 4;
@@ -109,11 +108,10 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bar_off);
   uint64_t* full = bars;                          // [8] TMA bytes landed
   uint64_t* empty = bars + BS_MAX_STAGES;         // [8] 4 converter warps + the output warp of the stage's pixel chunk
-  uint64_t* g_ready = bars + 2 * BS_MAX_STAGES;   // G of a tile is in TMEM (A operand of the du GEMMs)
+  uint64_t* g_ready = bars + 2 * BS_MAX_STAGES;   // G of a tile is in TMEM and shared memory
   uint64_t* g_tmem_free = g_ready + 1;            // the du GEMMs of a tile have read G from TMEM
-  uint64_t* gs_ready = g_ready + 2;               // [4] pixel chunk q of G is in shared memory (B operand of the dW GEMMs)
-  uint64_t* gs_free = gs_ready + BS_NQ;           // [4] the dW GEMMs of a tile have read chunk q
-  uint64_t* d2_full = gs_free + BS_NQ;            // [2]
+  uint64_t* g_smem_free = g_ready + 2;            // the dW GEMMs of a tile have read G from shared memory
+  uint64_t* d2_full = g_ready + 3;                // [2]
   uint64_t* d2_empty = d2_full + 2;               // [2] the four output warps have read the buffer
   uint64_t* a_full = d2_empty + 2;                // [2]
   uint64_t* a_empty = a_full + 2;                 // [2]
@@ -129,7 +127,11 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
     const float4* src = reinterpret_cast<const float4*>(w2g);
     float4* dst = reinterpret_cast<float4*>(sW2);
     for (int i = threadIdx.x; i < n4; i += BS_THREADS) dst[i] = src[i];
-    for (int i = threadIdx.x; i < 4 * OP; i += BS_THREADS) sCls[(i % OP) * 4 + i / OP] = cls_g[i];
+    // class constants per class PAIR: two float4 {pp0, pp1, an0, an1} {pa0, pa1, Bk0, Bk1} (operands of the packed derivative)
+    for (int i = threadIdx.x; i < 4 * OP; i += BS_THREADS) {
+      const int q = i / OP, k = i % OP;
+      sCls[(k >> 1) * 8 + q * 2 + (k & 1)] = cls_g[i];
+    }
     for (int i = threadIdx.x; i < 8 * 3 * OP; i += BS_THREADS) sRed[i] = 0.f;
     // rows NR..NP-1 of the G planes are addressed by the dW GEMM (N = NP) and never written: keep them finite
     float4* gz = reinterpret_cast<float4*>(sG);
@@ -137,8 +139,7 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 5); }
-    mbar_init(g_ready, 4); mbar_init(g_tmem_free, 1);
-    for (int q = 0; q < BS_NQ; ++q) { mbar_init(&gs_ready[q], 1); mbar_init(&gs_free[q], 1); }
+    mbar_init(g_ready, 4); mbar_init(g_tmem_free, 1); mbar_init(g_smem_free, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&d2_full[i], 1); mbar_init(&d2_empty[i], 4);
       mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1);
@@ -229,10 +230,10 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
         mbar_wait(acc_empty, (((uint32_t)(i / BS_DRAIN)) & 1u) ^ 1u);   // the previous chain has been drained
         tc_fence_after();
       }
+      mbar_wait(g_ready, (uint32_t)i & 1u);
       for (int g = 0; g < nblk; ++g) {
         const uint32_t acc = tb + BS_ACC_COL + g * NP;
         for (int q = 0; q < BS_NQ; ++q) {
-          if (g == 0) mbar_wait(&gs_ready[q], (uint32_t)i & 1u);   // chunk q of this tile's G has been written
           const uint32_t gq_hi = g_hi0 + (uint32_t)(q * NP * 128), gq_lo = g_lo0 + (uint32_t)(q * NP * 128);
 #pragma unroll
           for (int h = 0; h < 2; ++h, ++hc) {
@@ -252,16 +253,16 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
                 tc_mma_tf32_ts(acc, a_col + ks * 8, b_lo, idesc, 1u);
               }
               tc_commit(&a_empty[bf]);
-              if (h == 1 && g == nblk - 1) tc_commit(&gs_free[q]);   // last use of chunk q by this tile
             }
             __syncwarp();
           }
         }
       }
-      if (ci == BS_DRAIN - 1 || i == my_tiles - 1) {
-        if (elect_one_sync()) tc_commit(acc_full);
-        __syncwarp();
+      if (elect_one_sync()) {
+        tc_commit(g_smem_free);
+        if (ci == BS_DRAIN - 1 || i == my_tiles - 1) tc_commit(acc_full);
       }
+      __syncwarp();
     }
   }
   } else if (warp < 8) {
@@ -379,9 +380,9 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
       pT = pS + (size_t)OP * HW;
       n2 = __ldg(pS + (size_t)(2 * OP) * HW);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        Sn[e] = __ldcs(pS + e * hw);
-        Tn[e] = __ldcs(pT + e * hw);
+      for (int e = 0; e < 4; ++e) {      // rows of padded classes (k >= O) were never written by the forward: not read
+        Sn[e] = (e < O) ? __ldcs(pS + e * hw) : 0.f;
+        Tn[e] = (e < O) ? __ldcs(pT + e * hw) : 0.f;
         Gn[e] = (e < O) ? __ldcs(pG + e * hw) : 0.f;
       }
     };
@@ -395,7 +396,7 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
       if (i != wg) first_loads(i);
 #endif
       const PixelScalarGrads ps = tangent_scalar_grads(n2, hc);
-      float g_gamma = 0.f, g_t2 = 0.f, g_om = 0.f;
+      float2 g_gamma2 = make_float2(0.f, 0.f), g_t22 = g_gamma2, g_om2 = g_gamma2;
       float keepS[OP], keepT[OP];
 #pragma unroll 1
       for (int k0 = 0; k0 < OP; k0 += 4) {
@@ -404,26 +405,31 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
         const bool more = (k0 + 4 < OP);          // warp-uniform: the saved planes hold OP rows, dlogits only O
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
+          // padded classes (k >= O) carry zeros, and so does the upstream gradient of dead lanes: every quantity derived
+          // from them is then an exact zero
           Sc[e] = Sn[e]; Tc[e] = Tn[e]; Gc[e] = live ? Gn[e] : 0.f;
           if (more) {
-            Sn[e] = __ldcs(pS + e * hw);
-            Tn[e] = __ldcs(pT + e * hw);
-            Gn[e] = (k0 + 4 + e < O) ? __ldcs(pG + e * hw) : 0.f;
+            const bool valid = (k0 + 4 + e < OP - 3) || (k0 + 4 + e < O);   // warp-uniform, a compile-time truth but for 3 classes
+            Sn[e] = valid ? __ldcs(pS + e * hw) : 0.f;
+            Tn[e] = valid ? __ldcs(pT + e * hw) : 0.f;
+            Gn[e] = valid ? __ldcs(pG + e * hw) : 0.f;
           }
         }
         float gS[4], gT[4];
         float cs[16];     // class-scalar partials of the group: [class e][d_pp, d_an, d_pa], padded to 16
 #pragma unroll
-        for (int e = 0; e < 16; ++e) cs[e] = 0.f;
+        for (int e = 12; e < 16; ++e) cs[e] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = k0 + e;
-          gS[e] = gT[e] = 0.f;
-          if (k < OP - 3 || k < O) {   // warp-uniform; a compile-time truth for all but the last three classes
-            const float4 cl = reinterpret_cast<const float4*>(sCls)[k];
-            mlr_logit_grad(Gc[e], Sc[e], Tc[e], ps, cl.x, cl.y, cl.z, cl.w, hc, gS[e], gT[e], g_gamma, g_t2, g_om, cs[3 * e + 0],
-                           cs[3 * e + 1], cs[3 * e + 2]);
-          }
+        for (int j = 0; j < 2; ++j) {             // two class pairs on the packed fp32x2 pipe
+          const int kp = (k0 >> 1) + j;
+          const float4 c0 = reinterpret_cast<const float4*>(sCls)[2 * kp], c1 = reinterpret_cast<const float4*>(sCls)[2 * kp + 1];
+          float2 gs2, gt2, dpp = make_float2(0.f, 0.f), dan = dpp, dpa = dpp;
+          mlr_logit_grad2(make_float2(Gc[2 * j], Gc[2 * j + 1]), make_float2(Sc[2 * j], Sc[2 * j + 1]),
+                          make_float2(Tc[2 * j], Tc[2 * j + 1]), ps, make_float2(c0.x, c0.y), make_float2(c0.z, c0.w),
+                          make_float2(c1.x, c1.y), make_float2(c1.z, c1.w), hc, gs2, gt2, g_gamma2, g_t22, g_om2, dpp, dan, dpa);
+          gS[2 * j] = gs2.x; gS[2 * j + 1] = gs2.y; gT[2 * j] = gt2.x; gT[2 * j + 1] = gt2.y;
+          cs[6 * j + 0] = dpp.x; cs[6 * j + 1] = dan.x; cs[6 * j + 2] = dpa.x;
+          cs[6 * j + 3] = dpp.y; cs[6 * j + 4] = dan.y; cs[6 * j + 5] = dpa.y;
         }
         // warp reduction of the 12 partials by recursive halving: at every step a lane hands half of its values to its
         // partner and adds the partner's other half, so 8 + 4 + 2 + 1 + 1 shuffles replace 12 x 5 (fixed order: bitwise
@@ -464,11 +470,11 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
           }
         }
       }
+      const float g_gamma = g_gamma2.x + g_gamma2.y, g_t2 = g_t22.x + g_t22.y, g_om = g_om2.x + g_om2.y;
       const float alpha = live ? 2.f * (g_gamma * ps.dgam + g_t2 * ps.dt2 + g_om * ps.dom) : 0.f;
-      // The G buffers are single.  TMEM copy first, as soon as the du GEMMs of the previous tile (the other warpgroup's)
-      // have read theirs: the du GEMM of this tile's first channel block then runs while the previous tile is still
-      // streaming, and its D2 is waiting when this tile's first stage arrives.  The shared-memory copy follows chunk by
-      // chunk: warp wq owns pixel chunk wq and only waits for the previous tile's last dW GEMM on THAT chunk.
+      // The G buffers are single: wait until the GEMMs of the previous tile (the other warpgroup's) have read them.
+      // (Handing G over earlier -- TMEM first, shared memory chunk by chunk behind per-chunk barriers -- was tried in round 2:
+      // no gain, and intermittently wrong dP / dA on ragged images; profiles/r2_k4.md.)
       uint32_t sh[OP], sl[OP], th[OP], tl[OP];
 #pragma unroll
       for (int k = 0; k < OP; ++k) {
@@ -478,6 +484,7 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
         tl[k] = __float_as_uint(keepT[k] - __uint_as_float(th[k]));
       }
       mbar_wait(g_tmem_free, ((uint32_t)i & 1u) ^ 1u);
+      mbar_wait(g_smem_free, ((uint32_t)i & 1u) ^ 1u);
       tc_fence_after();
       {
         const uint32_t fg = tmem_base + lane_addr + BS_G_COL;
@@ -488,14 +495,8 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
           tmem_st_x4(fg + NP + 4 * k4, *reinterpret_cast<uint32_t(*)[4]>(&sl[4 * k4]));
           tmem_st_x4(fg + NP + OP + 4 * k4, *reinterpret_cast<uint32_t(*)[4]>(&tl[4 * k4]));
         }
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(g_ready);
-      mbar_wait(&gs_free[wq], ((uint32_t)i & 1u) ^ 1u);
-      {
-        // chunk wq, row n, this lane's pixel (conflict-free: a warp writes one 128-byte row per instruction)
+        // shared-memory copy for the dW GEMM: chunk wq, row n, this lane's pixel (conflict-free: a warp writes one
+        // 128-byte row per instruction)
         unsigned char* gq_hi = sG + (size_t)wq * NP * 128;
         unsigned char* gq_lo = gq_hi + L.g_plane;
 #pragma unroll
@@ -508,9 +509,11 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
           *reinterpret_cast<uint32_t*>(gq_lo + o_t) = tl[k];
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores of G -> visible to the dW GEMM
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&gs_ready[wq]);
+      if (lane == 0) mbar_arrive(g_ready);
 #ifndef HALO_BS_NO_PREFETCH
       if (i + 2 < my_tiles) first_loads(i + 2);     // in flight under the output pass below
 #endif

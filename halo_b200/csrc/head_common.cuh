@@ -366,6 +366,71 @@ __device__ __forceinline__ void mlr_logit_grad(float G, float S, float T, const 
   d_pa = fmaf(g_num, Anum, d_pa);
 }
 
+// The derivative for TWO classes at a time on the packed fp32x2 pipe (sm_100 FFMA2 / FADD2 / FMUL2): every multiply / add
+// of mlr_logit_grad is one packed instruction for the pair; comparisons, selects, min / max and MUFU stay scalar per half.
+// g_gamma / g_t2 / g_om accumulate per half (the caller adds the halves), the class-scalar partials come back per half.
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ void mlr_logit_grad2(float2 G, float2 S, float2 T, const PixelScalarGrads& ps, float2 pp, float2 an,
+                                                float2 pa, float2 Bk, const HeadConsts& hc, float2& gS, float2& gT,
+                                                float2& g_gamma, float2& g_t2, float2& g_om, float2& d_pp, float2& d_an,
+                                                float2& d_pa) {
+  const float2 gam = f2(ps.gamma);
+  const float2 px = __fmul2_rn(gam, S), xa = __fmul2_rn(gam, T);
+  const float2 cpx2 = __fmul2_rn(f2(2.f * hc.c), px);
+  const float2 one_cpx = __fadd2_rn(f2(1.f), cpx2);
+  const float2 Anum = __fadd2_rn(one_cpx, f2(ps.t2));
+  const float2 Draw = __ffma2_rn(f2(hc.c * ps.t2), pp, one_cpx);
+  const bool dc0 = Draw.x < 1e-12f, dc1 = Draw.y < 1e-12f;
+  const float2 D = make_float2(fmaxf(Draw.x, 1e-12f), fmaxf(Draw.y, 1e-12f));
+  const float2 num = __ffma2_rn(Bk, xa, __fmul2_rn(Anum, pa));
+  const float2 bo = __fmul2_rn(Bk, f2(ps.omega));
+  const float2 thr = __fmul2_rn(f2(hc.om_max), D);
+  const bool in0 = bo.x >= thr.x, in1 = bo.y >= thr.y;
+  const float2 dlo = __fmul2_rn(f2(1e-12f), D);
+  const float2 den = make_float2(fmaxf(bo.x, dlo.x), fmaxf(bo.y, dlo.y));
+  const float2 dmb = __fadd2_rn(D, neg2(bo));                                   // D * c * m
+  const float2 mthr = __fmul2_rn(D, f2(1e-24f * hc.c));
+  const bool mc0 = dmb.x <= mthr.x, mc1 = dmb.y <= mthr.y;                       // m clamped at 1e-24: no gradient through it
+  const float2 dmp = make_float2(fmaxf(dmb.x, 0.f), fmaxf(dmb.y, 0.f));
+  const float2 xo_a = __fmul2_rn(__fmul2_rn(D, dmp), f2(hc.inv_c));
+  const float2 xo_b = __fmul2_rn(__fmul2_rn(D, D), f2(1e-24f));
+  const float2 dd = __fmul2_rn(den, den);
+  const float x2a = in0 ? dd.x : fmaxf(xo_a.x, xo_b.x), x2b = in1 ? dd.y : fmaxf(xo_a.y, xo_b.y);
+  const float2 rinv = make_float2(fast_rsqrt(fmaxf(x2a, 1e-36f)), fast_rsqrt(fmaxf(x2b, 1e-36f)));
+  const float2 a_num = __fmul2_rn(make_float2(in0 ? hc.two_s : hc.out_scale, in1 ? hc.two_s : hc.out_scale), rinv);
+  const float2 arg = __fmul2_rn(num, a_num);
+  const float2 ar = __fmul2_rn(arg, rinv);
+  const float2 q = __fmul2_rn(__fmul2_rn(ar, rinv), f2(0.5f * hc.inv_c));       // arg / (2 c X2)
+  const float2 qD = __fmul2_rn(q, D);
+  const float2 a_bo = make_float2(in0 ? -ar.x : (mc0 ? 0.f : qD.x), in1 ? -ar.y : (mc1 ? 0.f : qD.y));
+  const float2 aD_raw = __fmul2_rn(neg2(q), __ffma2_rn(f2(2.f), D, neg2(bo)));
+  const float2 a_D = make_float2((in0 || dc0 || mc0) ? 0.f : aD_raw.x, (in1 || dc1 || mc1) ? 0.f : aD_raw.y);
+  // asinh(arg) and its derivative 1/sqrt(1 + arg^2) share the rsqrt
+  const float2 ax = make_float2(fabsf(arg.x), fabsf(arg.y));
+  const float2 v = __ffma2_rn(ax, ax, f2(1.f));
+  const float2 rs = make_float2(fast_rsqrt(v.x), fast_rsqrt(v.y));
+  const float2 tm = __ffma2_rn(v, rs, ax);
+  const float ta = (ax.x > 1e9f) ? 2.f * ax.x : tm.x, tb = (ax.y > 1e9f) ? 2.f * ax.y : tm.y;
+  const float2 ln = __fmul2_rn(make_float2(fast_lg2(ta), fast_lg2(tb)), f2(0.69314718056f));
+  const float2 ash = make_float2(copysignf(ln.x, arg.x), copysignf(ln.y, arg.y));
+  const float2 gl = __fmul2_rn(G, f2(hc.two_over_s));
+  const float2 g = __fmul2_rn(__fmul2_rn(gl, an), rs);
+  const float2 g_num = __fmul2_rn(g, a_num), g_bo = __fmul2_rn(g, a_bo), g_D = __fmul2_rn(g, a_D);
+  const float2 g_Bk = __ffma2_rn(g_num, xa, __fmul2_rn(g_bo, f2(ps.omega)));
+  const float2 g_xa = __fmul2_rn(g_num, Bk);
+  const float2 g_Anum = __fmul2_rn(g_num, pa);
+  const float2 g_cpx2 = __fadd2_rn(g_Anum, g_D);
+  g_t2 = __fadd2_rn(g_t2, __ffma2_rn(__fmul2_rn(g_D, f2(hc.c)), pp, g_Anum));
+  g_om = __ffma2_rn(g_bo, Bk, g_om);
+  const float2 g_px = __fmul2_rn(f2(2.f * hc.c), g_cpx2);
+  g_gamma = __fadd2_rn(g_gamma, __ffma2_rn(g_px, S, __fmul2_rn(g_xa, T)));
+  gS = __fmul2_rn(g_px, gam);
+  gT = __fmul2_rn(g_xa, gam);
+  d_pp = __fadd2_rn(d_pp, __fmul2_rn(f2(hc.c), __ffma2_rn(g_D, f2(ps.t2), neg2(g_Bk))));
+  d_an = __ffma2_rn(gl, ash, d_an);
+  d_pa = __ffma2_rn(g_num, Anum, d_pa);
+}
+
 // arguments shared by the CUDA-core and tensor-core forward kernels
 struct HeadArgs {
   const void* feat;

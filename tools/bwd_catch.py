@@ -1,0 +1,51 @@
+"""Catch a deviating launch of the streaming backward on a ragged shape and show WHICH partials differ from a good launch."""
+import os, sys, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import halo_b200
+from halo_b200 import synth, _native as nat
+dev = torch.device("cuda", 0)
+O, C, B = 19, 256, 3
+H = int(sys.argv[2]) if len(sys.argv) > 2 else 333
+W = int(sys.argv[3]) if len(sys.argv) > 3 else 500
+OP, KP, CPAD, CP, HW = 20, 40, 256, 256, H * W
+P, A = synth.head_params(O, C, seed=0, device=dev)
+feat = torch.stack([synth.image_features(i, C, H, W, device=dev) for i in range(B)])
+dl = torch.randn((B, O, H, W), device=dev, generator=torch.Generator(device=dev).manual_seed(1)) * 1e-3
+r = halo_b200.head_forward(feat, P, A, 1.0, want_logits=True, want_saved=True)
+def al(x): return (x + 255) // 256 * 256
+def parts():
+    ws = [v for k, v in nat.workspace._bufs.items() if k[2] == "head_bwd"][0]
+    off = al((CPAD * KP + 4 * OP) * 4)
+    off = al(off + B * (KP + 1) * HW * 4)
+    cls = ws[off:off + 148 * 3 * OP * 4].view(torch.float32).reshape(148, 3, OP).clone()
+    off = al(off + 148 * 2 * 3 * OP * 4)
+    dw = ws[off:off + 148 * KP * CP * 4].view(torch.float32).reshape(148, KP, CP).clone()
+    return cls, dw
+TPI = (HW + 127) // 128
+good = None
+caught = 0
+NIT = int(sys.argv[1]) if len(sys.argv) > 1 else 400
+for it in range(NIT):
+    out = [t.clone() for t in halo_b200.head_backward(feat, P, A, 1.0, dl, saved=r["saved"])]
+    torch.cuda.synchronize()
+    cls, dw = parts()
+    if good is None:
+        good = (out, cls, dw)
+        continue
+    if not all(torch.equal(a, b) for a, b in zip(out, good[0])):
+        print("launch", it, "deviates: dP %.2e dA %.2e du %.2e" % tuple(float((a - b).abs().max() / b.abs().max()) for a, b in ((out[1], good[0][1]), (out[2], good[0][2]), (out[0], good[0][0]))))
+        dc = (cls != good[1]); dd = (dw != good[2])
+        print(" cls_part differs in CTAs", dc.any(dim=2).any(dim=1).nonzero().flatten().tolist(), "entries", int(dc.sum()))
+        ctas = dd.any(dim=2).any(dim=1).nonzero().flatten().tolist()
+        print(" dw_part differs in CTAs", ctas, "entries", int(dd.sum()))
+        for b in ctas[:4]:
+            rows = dd[b].any(dim=1).nonzero().flatten().tolist(); cols = dd[b].any(dim=0).nonzero().flatten()
+            print("  CTA %d (tiles %s, last tile %d ragged=%s): rows %s cols %d..%d (%d) maxdiff %.3e vs max %.3e" % (
+                b, len(range(b, B * TPI, 148)), list(range(b, B * TPI, 148))[-1], [t for t in range(b, B * TPI, 148) if t % TPI == TPI - 1],
+                rows[:8] + ["..."] + rows[-3:], int(cols.min()), int(cols.max()), cols.numel(), float((dw[b] - good[2][b]).abs().max()), float(good[2][b].abs().max())))
+            print("   cols", cols.tolist())
+            d = (dw[b] - good[2][b])[:, cols]
+            print("   diff rows 0,1,20,21 :", [[round(float(x), 5) for x in d[r_]] for r_ in (0, 1, 20, 21)])
+        caught += 1
+        if caught >= 3: break
+print("caught", caught, "of", NIT)
