@@ -118,6 +118,13 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
   uint64_t* acc_full = a_empty + 2;
   uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_off);
+  // Number of stages the producer has issued so far.  The output warps visit only the stages of their own tiles and pixel
+  // chunk, so they do NOT see every phase of a ring slot's `full` barrier; a parity wait is then only sound once the slot's
+  // previous use is known to have completed -- which is exactly what "the producer has issued this stage" implies (it waited
+  // for the slot's `empty` phase, i.e. for converters that had waited for the previous landing).  Without this gate a warp
+  // that races ahead (dead lanes of a ragged tile store nothing) could pass on the stale parity, release the slot early and
+  // let the next load overwrite rows a slower consumer had not read yet (seen as rare wrong dP/dA or dfeat, round 2).
+  volatile uint32_t* issued = tmem_slot + 1;
   float* sCls = reinterpret_cast<float*>(smem + L.cls_off);
   float* sRed = reinterpret_cast<float*>(smem + L.red_off);       // [8 derivative warps][3][OP]
 
@@ -138,6 +145,7 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
     for (int i = threadIdx.x; i < 2 * L.g_plane / 16; i += BS_THREADS) gz[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   if (threadIdx.x == 0) {
+    *issued = 0u;
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 5); }
     mbar_init(g_ready, 4); mbar_init(g_tmem_free, 1); mbar_init(g_smem_free, 1);
     for (int i = 0; i < 2; ++i) {
@@ -170,7 +178,7 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
   if (warp == 0) {
     // =================== TMA producer ===================
     int s = 0;
-    uint32_t ph = 0;
+    uint32_t ph = 0, n_issued = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int n = tile / a.tiles_per_img;
@@ -178,7 +186,9 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
       for (int g = 0; g < nblk; ++g) {
         for (int q = 0; q < BS_NQ; ++q) {
           mbar_wait(&empty[s], ph ^ 1u);
+          ++n_issued;
           if (elect_one_sync()) {
+            *issued = n_issued;      // the slot's previous phase is complete: parity waits on full[s] are sound from here on
             mbar_arrive_expect_tx(&full[s], (uint32_t)(cb * BS_CHUNK * 4));
             tma_load_2d(ring + (size_t)s * BS_STAGE_BYTES, &tmap, p0 + q * BS_CHUNK, n * C + g * 128, &full[s]);
           }
@@ -284,8 +294,6 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const float4*>(row + ((j ^ (ch & 7)) << 4));
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[s]);   // this warp's rows of the stage are in registers
 #pragma unroll
           for (int h = 0; h < 2; ++h, ++hc) {
             const int bf = (int)(hc & 1);
@@ -313,7 +321,14 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
               tc_fence_before();
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[bf]);
+            if (lane == 0) {
+              mbar_arrive(&a_full[bf]);
+              // The stage is released only here, after the conversion has CONSUMED every loaded register.  Releasing it
+              // right behind the eight LDS.128 (nothing had read their results yet) let the arrive overtake the loads once
+              // in ~1e9 hand-overs: the next TMA load then rewrote rows this warp had not fetched, and dP / dA came out
+              // wrong in a few channels of one CTA (round 2, tools/bwd_catch.py; any added use of v[] hid it).
+              if (h == 1) mbar_arrive(&empty[s]);
+            }
           }
           if (++s == NST) { s = 0; ph ^= 1u; }
         }
@@ -524,6 +539,7 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
         const int sc = (i * nblk + g) * BS_NQ + wq;
         const int s = sc % NST;
         const int bc = i * nblk + g, db = bc & 1;
+        while (*issued <= (uint32_t)sc) {}      // see `issued` above
         mbar_wait(&full[s], (uint32_t)(sc / NST) & 1u);
         mbar_wait(&d2_full[db], ((uint32_t)bc >> 1) & 1u);
         tc_fence_after();
