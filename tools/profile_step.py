@@ -28,7 +28,7 @@ for _ in range(args.steps):
         halo_b200.head_forward(d["feat"], P, A, 1.0, want_logits=True, want_radius=True)
     else:
         dl = torch.randn((args.batch, O, H, W), device=dev) * 1e-3
-        halo_b200.head_forward(d["feat"], P, A, 1.0, want_logits=True)
-        halo_b200.head_backward(d["feat"], P, A, 1.0, dl)
+        r = halo_b200.head_forward(d["feat"], P, A, 1.0, want_logits=True, want_saved=True)   # the training step of bench.py
+        halo_b200.head_backward(d["feat"], P, A, 1.0, dl, saved=r["saved"])
 torch.cuda.synchronize()
 print("done")
