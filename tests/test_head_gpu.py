@@ -344,3 +344,30 @@ def test_backward_streaming_kernel(shape, monkeypatch):
     assert rel_err(dP, dP_ref) <= 1e-4 and rel_err(dA, dA_ref) <= 1e-4
     du2, dP2, dA2 = halo_b200.head_backward(ud, Pd, Ad, 1.0, dl.to(DEV))  # recompute instead of saved planes: same bits
     assert torch.equal(du, du2) and torch.equal(dP, dP2) and torch.equal(dA, dA2)
+
+
+@pytest.mark.parametrize("case", [(256, 3, 333, 500, 0), (256, 3, 320, 500, 4), (128, 3, 333, 500, 0), (64, 4, 328, 500, 12)],
+                         ids=["c256-ragged", "c256-misaligned", "c128-ragged", "c64-ragged-misaligned"])
+def test_backward_streaming_kernel_is_reproducible_over_many_launches(case, monkeypatch):
+    """The per-CTA partials are added in a fixed order, so EVERY launch must return the same bits.  This is the regression test
+    of a round-2 race (a ring stage released before its rows had been consumed: once per ~1 000 launches a few channels of
+    one CTA's dP / dA partial were built from the next load's rows; profiles/r2_k4.md): 600 launches on shapes whose
+    ragged last tiles and 16-byte-misaligned feature rows exposed it most often, each compared bit for bit with the first."""
+    for k in ("HALO_BWD_CUDA_CORE", "HALO_BWD_DW_CUDA_CORE", "HALO_BWD_TWO_KERNEL"):
+        monkeypatch.delenv(k, raising=False)
+    C, N, H, W, off = case
+    O = 19
+    P, A = synth.head_params(O, C, seed=0, device=DEV)
+    store = torch.empty(N * C * H * W + off, device=DEV)
+    feat = store[off:].view(N, C, H, W)
+    for i in range(N):
+        feat[i] = synth.image_features(i, C, H, W, device=DEV)
+    dl = torch.randn((N, O, H, W), device=DEV, generator=torch.Generator(device=DEV).manual_seed(1)) * 1e-3
+    fwd = halo_b200.head_forward(feat, P, A, 1.0, want_logits=True, want_saved=True)
+    first = [t.clone() for t in halo_b200.head_backward(feat, P, A, 1.0, dl, saved=fwd["saved"])]
+    bad = torch.zeros((), dtype=torch.int32, device=DEV)
+    for _ in range(600):
+        out = halo_b200.head_backward(feat, P, A, 1.0, dl, saved=fwd["saved"])
+        for a, b in zip(out, first):
+            bad += (a != b).any()
+    assert int(bad) == 0
