@@ -41,6 +41,11 @@ constexpr int TC_STAGES = TC_WG_STAGES * 2;
 constexpr int TC_STAGE_FLOATS = TC_BK * TC_BM;
 constexpr int TC_NWG = 2;       // converter warpgroups (each owns a TMA ring, an MMA issuer, A buffers and accumulators)
 constexpr int TC_THREADS = 128 + 128 * TC_NWG + 128;  // control warps + converters + one epilogue warpgroup
+// A second epilogue warpgroup (NEPI = 2: 640 threads, epilogue warpgroup e finishes the tiles of converter warpgroup e) is
+// used for C <= 128: the epilogue costs the same per pixel whatever C is, so with a quarter / half of the conversion work
+// per pixel the single epilogue warpgroup paces the kernel (C = 64, the channel count of every shipped HALO config: 44 % of
+// the HBM roofline with one, see profiles/r2_k1.md).  At C = 256 the SM's total issue bandwidth is the limit and one is as good.
+constexpr int tc_threads(int nepi) { return 128 + 128 * TC_NWG + 128 * nepi; }
 constexpr int TC_TMEM_COLS = 512;
 #ifndef HALO_TC_HK
 #define HALO_TC_HK 16
@@ -86,8 +91,8 @@ __host__ __device__ inline TcSmemLayout tc_smem_layout(int NP, int OP, int C) {
 //   * the two cross terms lo.hi + hi.lo (2^-11 of the main term, so their rounding is harmless) share one
 //     "correction" accumulator;
 // the epilogue adds the NMAIN+1 partial results in fp32 registers.
-template <int NP, int OP, int NMAIN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int NP, int OP, int NMAIN, int NEPI>
+__global__ void __launch_bounds__(tc_threads(NEPI), 1)
 head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, const float* __restrict__ wtc) {
   constexpr int NACC = NMAIN + 1;  // accumulator NMAIN is the correction accumulator
   static_assert(TC_ACC_COL0 + TC_NWG * NACC * NP <= TC_TMEM_COLS, "TMEM column budget");
@@ -115,10 +120,10 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     const int n4 = 2 * NR * C / 4;
     const float4* src = reinterpret_cast<const float4*>(wtc);
     float4* dst = reinterpret_cast<float4*>(sW);
-    for (int i = threadIdx.x; i < n4; i += TC_THREADS) dst[i] = src[i];
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = src[i];
     // [4][OP] -> per class PAIR two float4 {pp0, pp1, an0, an1} {pa0, pa1, Bk0, Bk1} (operands of the packed epilogue)
     const float* csrc = wtc + (size_t)2 * NR * C;
-    for (int i = threadIdx.x; i < 4 * OP; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < 4 * OP; i += blockDim.x) {
       const int q = i / OP, k = i % OP;
       sCls[(k >> 1) * 8 + q * 2 + (k & 1)] = csrc[i];
     }
@@ -160,6 +165,11 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
     my_tiles = rounds * TC_NWG + (tail <= 0 ? 0 : (tail >= TC_NWG ? TC_NWG : tail));
   }
 
+  // NEPI = 2: 640 threads start with 96 registers each; the roles then trade them (setmaxnreg is warpgroup-wide and sits
+  // at the top of each role's region, no control-flow merge behind it): control 40, converters 80, epilogue 136
+  // (128 x 40 + 256 x 80 + 256 x 136 = 60 416 <= 640 x 96).
+  if (warp < 4) {
+  if (NEPI == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0 || warp == 2) {
     // =================== TMA producers: warp 0 feeds warpgroup 0, warp 2 feeds warpgroup 1 ===================
     // Each warpgroup owns a private ring (stages + barriers): a barrier then has exactly one producer and one
@@ -233,8 +243,10 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
         __syncwarp();
       }
     }
+  }
   } else if (warp >= 4 && warp < 4 + 4 * TC_NWG) {
     // =================== converter warpgroups (thread = pixel = TMEM lane) ===================
+    if (NEPI == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     const int g = (warp - 4) >> 2;
     const int wq = warp & 3;                   // TMEM lane quarter this warp may touch
     const int m = wq * 32 + lane;              // pixel row inside the tile
@@ -269,12 +281,16 @@ head_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap, const HeadArgs a, c
       }
     }
   } else if (warp >= 4 + 4 * TC_NWG) {
-    // =================== epilogue warpgroup: every tile, in order ===================
+    // =================== epilogue warpgroup(s): NEPI = 1 every tile in order; NEPI = 2 warpgroup e the tiles of converter
+    // warpgroup e (accumulators, |u|^2 and their barriers are per converter warpgroup already) ===================
+    if (NEPI == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 136;");
+    const int epi = (warp - (4 + 4 * TC_NWG)) >> 2;
     const int wq = warp & 3;
     const int m = wq * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
     const HeadConsts hc = a.hc;
-    for (int i = 0; i < my_tiles; ++i) {
+    static_assert(NEPI == 1 || NEPI == TC_NWG, "one epilogue warpgroup, or one per converter warpgroup");
+    for (int i = (NEPI == 1 ? 0 : epi); i < my_tiles; i += NEPI) {
       const int g = i % TC_NWG, it = i / TC_NWG;
       const int tile = tc_tile_of(i, blockIdx.x, gridDim.x);
       const int n = tile / a.tiles_per_img;
@@ -449,8 +465,15 @@ static int launch_tc(const CUtensorMap& tmap, const HeadArgs& a, const float* wt
   constexpr int FIT = (TC_TMEM_COLS - TC_ACC_COL0) / (TC_NWG * NP) - 1;
   constexpr int NMAIN = FIT > 8 ? 8 : FIT;
   static_assert(NMAIN >= 1, "TMEM budget");
-  HALO_CUDA(cudaFuncSetAttribute(head_fwd_tc_kernel<NP, OP, NMAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  head_fwd_tc_kernel<NP, OP, NMAIN><<<grid, TC_THREADS, smem, st>>>(tmap, a, wtc);
+  static const int force = [] { const char* e = getenv("HALO_TC_NEPI"); return e ? atoi(e) : 0; }();   // A/B knob: 1 | 2
+  const bool two = force ? (force == 2) : (a.C <= 128);
+  if (two) {
+    HALO_CUDA(cudaFuncSetAttribute(head_fwd_tc_kernel<NP, OP, NMAIN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_fwd_tc_kernel<NP, OP, NMAIN, 2><<<grid, tc_threads(2), smem, st>>>(tmap, a, wtc);
+  } else {
+    HALO_CUDA(cudaFuncSetAttribute(head_fwd_tc_kernel<NP, OP, NMAIN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    head_fwd_tc_kernel<NP, OP, NMAIN, 1><<<grid, tc_threads(1), smem, st>>>(tmap, a, wtc);
+  }
   return launch_status("head_fwd_tc_kernel");
 }
 

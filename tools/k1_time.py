@@ -7,7 +7,8 @@ from halo_b200 import synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 O = int(sys.argv[2]) if len(sys.argv) > 2 else 19
 dev = "cuda:0"
-C, H, W = 256, 640, 1280
+C = int(sys.argv[3]) if len(sys.argv) > 3 and sys.argv[3].isdigit() else 256
+H, W = 640, 1280
 P, A = synth.head_params(O, C, seed=0, device=dev)
 feat = torch.empty((B, C, H, W), device=dev)
 for i in range(B):
@@ -22,4 +23,4 @@ for tc in (True, False) if "--cc" in sys.argv else (True,):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 5
     gbs = 4.0 * C * B * H * W / ms / 1e6
-    print(json.dumps({"lib": os.environ.get("HALO_B200_LIB", "default"), "tensor_cores": tc, "batch": B, "classes": O, "ms": round(ms, 3), "GB/s": round(gbs, 1), "frac_of_6547.5": round(gbs / 6547.5, 4)}))
+    print(json.dumps({"lib": os.environ.get("HALO_B200_LIB", "default"), "tensor_cores": tc, "batch": B, "classes": O, "C": C, "ns_per_px": round(ms * 1e6 / (B * H * W), 4), "ms": round(ms, 3), "GB/s": round(gbs, 1), "frac_of_6547.5": round(gbs / 6547.5, 4)}))
