@@ -413,11 +413,40 @@ head_bwd_stream_kernel(const __grid_constant__ CUtensorMap tmap, const BsArgs a,
       const PixelScalarGrads ps = tangent_scalar_grads(n2, hc);
       float2 g_gamma2 = make_float2(0.f, 0.f), g_t22 = g_gamma2, g_om2 = g_gamma2;
       float keepS[OP], keepT[OP];
+#ifndef HALO_BS_NO_L2_PREFETCH
+      // The in-loop loads below run one class group ahead (~400 cycles of math), less than a DRAM round trip under load
+      // (r2i profile: 15 % of all stall samples sat on them).  So the rows of this warpgroup's NEXT tile are pulled into L2
+      // while this tile is differentiated -- one prefetch per row, no registers held -- and the loads then cost an L2 hit.
+      // Measured (batch 8, profiles/r2_k4.md): C = 128 backward 2.16 -> 1.98 ms, C = 64 1.60 -> 1.59 ms, but C = 256
+      // 3.03 -> 3.24 ms (the feature stream already saturates the memory system there), hence C <= 128 only.
+      const bool pf = (i + 2 < my_tiles) && (C <= 128);          // warp-uniform
+      long long dS = 0, dG = 0;                    // element offsets from this tile's pointers to the next own tile's
+      if (pf) {
+        const int tile2 = tile + 2 * (int)gridDim.x;
+        const int n2i = tile2 / a.tiles_per_img;
+        const int p2 = (tile2 - n2i * a.tiles_per_img) * BS_BM + m;
+        const int pc = live ? p : HW - 1, pc2 = (p2 < HW) ? p2 : HW - 1;
+        dS = (long long)(n2i - n) * SVR * HW + (pc2 - pc);
+        dG = (long long)(n2i - n) * O * HW + (pc2 - pc);
+      }
+#endif
 #pragma unroll 1
       for (int k0 = 0; k0 < OP; k0 += 4) {
         float Sc[4], Tc[4], Gc[4];
         pS += 4 * hw; pT += 4 * hw; pG += 4 * hw;
         const bool more = (k0 + 4 < OP);          // warp-uniform: the saved planes hold OP rows, dlogits only O
+#ifndef HALO_BS_NO_L2_PREFETCH
+        if (pf && more && (lane == 0 || lane == 31)) {      // a warp's 32 pixels of a row are one or two 128-byte lines
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if ((k0 + 4 + e < OP - 3) || (k0 + 4 + e < O)) {
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pS + e * hw + dS));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pT + e * hw + dS));
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(pG + e * hw + dG));
+            }
+          }
+        }
+#endif
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           // padded classes (k >= O) carry zeros, and so does the upstream gradient of dead lanes: every quantity derived
