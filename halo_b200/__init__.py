@@ -7,7 +7,7 @@ Mirrors the reference's Python call surface for that path and nothing else:
     core/active/build.py           -> halo_b200.active           (select_pixels_to_label, RegionSelection)
     mask / indicator files         -> halo_b200.maskio           (build.py:162-166, cityscapes.py:234,245-251)
     CE + negative-learning loss    -> halo_b200.losses           (train_learners.py:343-356, loss/negative_learning_loss.py)
-    conv_reduce + HFR (eval mode)  -> halo_b200.hfr              (models/classifier.py:526-550)
+    conv_reduce + HFR (eval/train) -> halo_b200.hfr              (models/classifier.py:526-550)
 
 All arithmetic runs in hand-written CUDA behind the C ABI of include/halo_b200.h
 (halo_b200/libhalo_sm100.so); there is no CPU path and no fallback.

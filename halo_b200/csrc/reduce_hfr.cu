@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(RH_THREADS) reduce_kernel(const ReduceArgs a) 
 #pragma unroll
   for (int j = 0; j < 4; ++j) sSq[tx][ty * 4 + j] = sq[j];
   __syncthreads();
-  if (threadIdx.x < RH_TC && cb + threadIdx.x < a.C) {
+  if (a.part_sq != nullptr && threadIdx.x < RH_TC && cb + threadIdx.x < a.C) {
     float s = 0.f;
     for (int q = 0; q < 16; ++q) s += sSq[q][threadIdx.x];
     a.part_sq[((size_t)n * a.tiles + tile) * a.C + cb + threadIdx.x] = s;
@@ -154,6 +154,7 @@ struct ScaleArgs {
   const float* W2;        // [C,C]
   const float* b2;        // [C]
   float* scale;           // [N][C] out (diagnostic / tests)
+  float* small;           // [N][3][C] | NULL: hbar, tbar (before the clamp), |y|  -- what the training backward needs
   int N, C, HW, tiles, blocks;
 };
 
@@ -173,6 +174,11 @@ __global__ void hfr_scale_kernel(const ScaleArgs a) {
     for (int t = 0; t < a.tiles; ++t) sq += a.part_sq[((size_t)n * a.tiles + t) * a.C + c];
     float wt = a.b2[c];
     for (int j = 0; j < a.C; ++j) wt = fmaf(a.W2[(size_t)c * a.C + j], hbar[j], wt);
+    if (a.small != nullptr) {
+      a.small[((size_t)n * 3 + 0) * a.C + c] = hbar[c];
+      a.small[((size_t)n * 3 + 1) * a.C + c] = wt;
+      a.small[((size_t)n * 3 + 2) * a.C + c] = sqrtf(sq);
+    }
     wt = fmaxf(wt, 1e-5f);                         // torch.clamp(norm_weights, min=1e-5)   (:542)
     a.scale[(size_t)n * a.C + c] = wt / fmaxf(sqrtf(sq), 1e-12f);   // F.normalize eps        (:546)
   }
@@ -191,6 +197,327 @@ __global__ void hfr_apply_kernel(float* __restrict__ y, const float* __restrict_
 __global__ void hfr_apply_scalar_kernel(float* __restrict__ y, const float* __restrict__ scale, int HW, long long total) {
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x)
     y[g] *= scale[g / HW];
+}
+
+
+// =====================================================================================================================
+// Training mode (the training step's side of classifier.py:526-550): BatchNorm1d normalises with the
+// statistics of the batch (all N*h*w rows), and autograd runs back through the re-weighting, the normalisation and the
+// 1x1 convolution.  Forward = the kernels above with the batch statistics folded in, plus hidden_stats_kernel; backward:
+//   dwt[n,c] = <dz, y_hat> ; dy1 = wt/|y| (dz - y_hat dwt)                               (normalise * weight)
+//   dtbar = dwt [tbar >= 1e-5] ; dW2 = sum_n dtbar (x) hbar ; db2 = sum_n dtbar ; v[n,:] = W2^T dtbar[n] / HW  (mean, Linear 2)
+//   g = v [b > 0] ; dbeta = sum g ; dgamma = sum g x_hat ; da = gamma/sigma (g - dbeta/M - x_hat dgamma/M)   (ReLU, BatchNorm)
+//   dW1 = sum da (x) y ; db1 = sum da ; dy = dy1 + W1^T da                                (Linear 1)
+//   df = Wr^T dy ; dWr = sum dy (x) f ; dbr = sum dy                                        (1x1 convolution)
+// Every sum over pixels goes through per-block partials and a fixed-order finish: bitwise reproducible.
+// =====================================================================================================================
+
+// per warp of 32 pixels and hidden unit j: (sum, M2 about the warp mean) of a = W1 y + b1 -- combined with Chan's formula
+// in double by hidden_stats_finish_kernel (a one-pass E[a^2] - mean^2 in fp32 loses the variance when |mean| >> sigma)
+template <int CMAX>
+__global__ void __launch_bounds__(128) hidden_stats_kernel(const HiddenArgs a, float* __restrict__ part /* [N][blocks][4 warps][2][C] */) {
+  extern __shared__ float sm[];
+  float* sW1 = sm;   // [C][C]
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < a.C * a.C; i += 128) sW1[i] = a.W1[i];
+  __syncthreads();
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  const bool live = p < a.HW;
+  float yv[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) yv[c] = (live && c < a.C) ? a.y[((size_t)n * a.C + c) * a.HW + p] : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cnt = __popc(__ballot_sync(0xffffffffu, live));
+  float* o = part + (((size_t)n * a.blocks + blockIdx.x) * 4 + warp) * 2 * a.C;
+  for (int j = 0; j < a.C; ++j) {
+    const float* wr = sW1 + (size_t)j * a.C;
+    float t = a.b1[j];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < a.C) t = fmaf(wr[c], yv[c], t);
+    float s = live ? t : 0.f;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    const float mean = cnt ? s / (float)cnt : 0.f;
+    float d = live ? (t - mean) : 0.f;
+    d *= d;
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o2);
+    if (lane == 0) { o[j] = s; o[a.C + j] = d; }
+  }
+}
+
+// one block: combine the warp partials in a fixed order (Chan et al.), fold the batch statistics into scale / shift
+__global__ void hidden_stats_finish_kernel(const float* __restrict__ part, int groups /* N*blocks*4 */, int HW, int blocks, int C,
+                                           const float* g, const float* b, float eps, float* bn /* [2][C] */, float* stats /* [2][C] */) {
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
+    double n_tot = 0.0, mean = 0.0, M2 = 0.0;
+    for (int q = 0; q < groups; ++q) {
+      const int blk = (q / 4) % blocks, w = q & 3;
+      int cnt = HW - (blk * 128 + w * 32);
+      cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
+      if (cnt == 0) continue;
+      const double s = part[(size_t)q * 2 * C + j], m2 = part[(size_t)q * 2 * C + C + j];
+      const double mb = s / cnt, delta = mb - mean, nn = n_tot + cnt;
+      M2 += m2 + delta * delta * n_tot * cnt / nn;
+      mean += delta * cnt / nn;
+      n_tot = nn;
+    }
+    const double var = M2 / n_tot;   // biased, what BatchNorm normalises with
+    const float sc = (float)((double)g[j] / sqrt(var + (double)eps));
+    bn[j] = sc;
+    bn[C + j] = (float)((double)b[j] - mean * (double)sc);
+    stats[j] = (float)mean;
+    stats[C + j] = (float)var;
+  }
+}
+
+__global__ void hfr_apply_oop_kernel(const float* __restrict__ y, const float* __restrict__ scale, float* __restrict__ z, int HW,
+                                     long long total) {
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (long long)gridDim.x * blockDim.x)
+    z[g] = y[g] * scale[g / HW];
+}
+
+// q[plane] = sum_p a[plane][p] * b[plane][p], one block per (n, c) plane, fixed-order tree
+__global__ void __launch_bounds__(256) dot_planes_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ q, int HW) {
+  __shared__ float red[256];
+  const size_t base = (size_t)blockIdx.x * HW;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) s = fmaf(a[base + p], b[base + p], s);
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) q[blockIdx.x] = red[0];
+}
+
+struct HfrSmallArgs {
+  const float* q;        // [N][C]  <dz, y>
+  const float* small;    // [N][3][C]  hbar, tbar (before the clamp), |y|
+  const float* W2;       // [C][C]
+  float* coef;           // [N][2][C]  dy1 = coef0 * dz - coef1 * y
+  float* v;              // [N][C]     dL/dh of every pixel of image n
+  float* dW2;            // [C][C]
+  float* db2;            // [C]
+  int N, C, HW;
+};
+// one block: the per-image scalars of the backward
+__global__ void hfr_bwd_small_kernel(const HfrSmallArgs a) {
+  extern __shared__ float sm[];
+  float* dtb = sm;   // [N][C]
+  const int C = a.C;
+  for (int i = threadIdx.x; i < a.N * C; i += blockDim.x) {
+    const int n = i / C, c = i - n * C;
+    const float tbar = a.small[((size_t)n * 3 + 1) * C + c], yn = a.small[((size_t)n * 3 + 2) * C + c];
+    const float wt = fmaxf(tbar, 1e-5f);
+    const float den = fmaxf(yn, 1e-12f);
+    const float dwt = a.q[i] / den;                    // <dz, y_hat>
+    dtb[i] = (tbar >= 1e-5f) ? dwt : 0.f;              // clamp(min) passes the gradient where the input is >= min
+    const float sc = wt / den;
+    a.coef[((size_t)n * 2 + 0) * C + c] = sc;
+    a.coef[((size_t)n * 2 + 1) * C + c] = (yn > 1e-12f) ? sc * dwt / den : 0.f;   // below eps F.normalize divides by a constant
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.N * C; i += blockDim.x) {
+    const int n = i / C, j = i - n * C;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s = fmaf(a.W2[(size_t)c * C + j], dtb[n * C + c], s);
+    a.v[i] = s / (float)a.HW;
+  }
+  for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+    const int c = i / C, j = i - c * C;
+    float s = 0.f;
+    for (int n = 0; n < a.N; ++n) s = fmaf(dtb[n * C + c], a.small[((size_t)n * 3 + 0) * C + j], s);
+    a.dW2[i] = s;
+  }
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int n = 0; n < a.N; ++n) s += dtb[n * C + c];
+    a.db2[c] = s;
+  }
+}
+
+struct HfrBnArgs {
+  const float* y;        // [N][C][HW]
+  const float* W1;       // [C][C]
+  const float* b1;       // [C]
+  const float* bn;       // [2][C] scale = gamma/sigma, shift = beta - mean*scale   (batch statistics)
+  const float* stats;    // [2][C] batch mean, biased variance
+  const float* v;        // [N][C]
+  float eps;
+  float* part;           // [N][blocks][2][C]  sum g, sum g*x_hat
+  int N, C, HW, blocks;
+};
+template <int CMAX>
+__global__ void __launch_bounds__(128) hfr_bwd_bn_sums_kernel(const HfrBnArgs a) {
+  extern __shared__ float sm[];
+  float* sW1 = sm;                          // [C][C]
+  float* sRed = sm + (size_t)a.C * a.C;     // [4 warps][2][C]
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < a.C * a.C; i += 128) sW1[i] = a.W1[i];
+  __syncthreads();
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  const bool live = p < a.HW;
+  float yv[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) yv[c] = (live && c < a.C) ? a.y[((size_t)n * a.C + c) * a.HW + p] : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int j = 0; j < a.C; ++j) {
+    const float* wr = sW1 + (size_t)j * a.C;
+    float t = a.b1[j];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < a.C) t = fmaf(wr[c], yv[c], t);
+    const float bval = fmaf(t, a.bn[j], a.bn[a.C + j]);
+    const float xh = (t - a.stats[j]) * rsqrtf(a.stats[a.C + j] + a.eps);
+    float g = (live && bval > 0.f) ? a.v[(size_t)n * a.C + j] : 0.f;
+    float gx = g * xh;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      g += __shfl_xor_sync(0xffffffffu, g, o);
+      gx += __shfl_xor_sync(0xffffffffu, gx, o);
+    }
+    if (lane == 0) { sRed[(warp * 2 + 0) * a.C + j] = g; sRed[(warp * 2 + 1) * a.C + j] = gx; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * a.C; i += 128) {
+    float s = 0.f;
+    for (int w = 0; w < 4; ++w) s += sRed[(size_t)w * 2 * a.C + i];
+    a.part[((size_t)n * a.blocks + blockIdx.x) * 2 * a.C + i] = s;
+  }
+}
+// fixed-order finish of [groups][rows] partials in double: out[i] = sum_g part[g][i]
+__global__ void sum_partials_kernel(const float* __restrict__ part, int groups, int rows, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int g = 0; g < groups; ++g) s += part[(size_t)g * rows + i];
+    out[i] = (float)s;
+  }
+}
+
+struct HfrDaArgs {
+  const float* y;        // [N][C][HW]
+  const float* dz;       // [N][C][HW]
+  const float* W1;
+  const float* b1;
+  const float* bn;       // [2][C]
+  const float* stats;    // [2][C]
+  const float* v;        // [N][C]
+  const float* dbg;      // [2][C] dbeta, dgamma
+  const float* coef;     // [N][2][C]
+  float eps;
+  float* da;             // [N][C][HW]
+  float* dy;             // [N][C][HW]
+  int N, C, HW;
+  float inv_m;           // 1 / (N*HW)
+};
+// thread = pixel: da (for dW1 / db1) and dy = dy1 + W1^T da
+template <int CMAX>
+__global__ void __launch_bounds__(128) hfr_bwd_da_kernel(const HfrDaArgs a) {
+  extern __shared__ float sm[];
+  float* sW1 = sm;   // [C][C]
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < a.C * a.C; i += 128) sW1[i] = a.W1[i];
+  __syncthreads();
+  const int p = blockIdx.x * 128 + threadIdx.x;
+  if (p >= a.HW) return;
+  float yv[CMAX], dyv[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    yv[c] = (c < a.C) ? a.y[((size_t)n * a.C + c) * a.HW + p] : 0.f;
+    dyv[c] = 0.f;
+  }
+  for (int j = 0; j < a.C; ++j) {
+    const float* wr = sW1 + (size_t)j * a.C;
+    float t = a.b1[j];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < a.C) t = fmaf(wr[c], yv[c], t);
+    const float bval = fmaf(t, a.bn[j], a.bn[a.C + j]);
+    const float xh = (t - a.stats[j]) * rsqrtf(a.stats[a.C + j] + a.eps);
+    const float g = (bval > 0.f) ? a.v[(size_t)n * a.C + j] : 0.f;
+    const float d = a.bn[j] * (g - a.dbg[j] * a.inv_m - xh * a.dbg[a.C + j] * a.inv_m);   // bn[j] = gamma / sigma
+    a.da[((size_t)n * a.C + j) * a.HW + p] = d;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < a.C) dyv[c] = fmaf(wr[c], d, dyv[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    if (c < a.C) {
+      const size_t o = ((size_t)n * a.C + c) * a.HW + p;
+      const float c0 = a.coef[((size_t)n * 2 + 0) * a.C + c], c1 = a.coef[((size_t)n * 2 + 1) * a.C + c];
+      a.dy[o] = fmaf(c0, a.dz[o], fmaf(-c1, yv[c], dyv[c]));
+    }
+  }
+}
+
+// Reduction over pixels: part[n][chunk][i][j] = sum_{p in chunk} A[n][i][p] * B[n][j][p], and rsum[n][chunk][i] = sum_p A[n][i][p]
+// (dW1 / db1 with A = da, B = y; dWr / dbr with A = dy, B = f).  64 x 64 output tiles, 32 pixels per shared-memory stage.
+struct GramArgs {
+  const float* A;   // [N][Ca][HW]
+  const float* B;   // [N][Cb][HW]
+  float* part;      // [N*chunks][Ca][Cb]
+  float* rsum;      // [N*chunks][Ca] | NULL
+  int Ca, Cb, HW, chunk, chunks;
+};
+__global__ void __launch_bounds__(256) gram_px_kernel(const GramArgs a) {
+  __shared__ float sA[32][64 + 1];   // [px][row]
+  __shared__ float sB[32][64 + 1];
+  const int n = blockIdx.z / a.chunks, ch = blockIdx.z - n * a.chunks;
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // ty: rows of A, tx: rows of B
+  const int p_lo = ch * a.chunk, p_hi = min(a.HW, p_lo + a.chunk);
+  float acc[4][4];
+  float rs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const float* An = a.A + (size_t)n * a.Ca * a.HW;
+  const float* Bn = a.B + (size_t)n * a.Cb * a.HW;
+  for (int p0 = p_lo; p0 < p_hi; p0 += 32) {
+    for (int t = threadIdx.x; t < 64 * 32; t += 256) {
+      const int r = t >> 5, px = t & 31;     // 32 consecutive pixels of one row: coalesced
+      const bool okp = p0 + px < p_hi;
+      sA[px][r] = (okp && i0 + r < a.Ca) ? __ldg(An + (size_t)(i0 + r) * a.HW + p0 + px) : 0.f;
+      sB[px][r] = (okp && j0 + r < a.Cb) ? __ldg(Bn + (size_t)(j0 + r) * a.HW + p0 + px) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int px = 0; px < 32; ++px) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { av[i] = sA[px][ty * 4 + i]; bv[i] = sB[px][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rs[i] += av[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+  float* o = a.part + (size_t)blockIdx.z * a.Ca * a.Cb;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (i0 + ty * 4 + i < a.Ca && j0 + tx * 4 + j < a.Cb) o[(size_t)(i0 + ty * 4 + i) * a.Cb + j0 + tx * 4 + j] = acc[i][j];
+  if (a.rsum != nullptr && blockIdx.x == 0 && tx == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i0 + ty * 4 + i < a.Ca) a.rsum[(size_t)blockIdx.z * a.Ca + i0 + ty * 4 + i] = rs[i];
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc) {   // out[c][r] = in[r][c]
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < R * Cc; i += gridDim.x * blockDim.x) {
+    const int r = i / Cc, c = i - r * Cc;
+    out[(size_t)c * R + r] = in[i];
+  }
 }
 
 }  // namespace halo
@@ -265,6 +592,7 @@ extern "C" int halo_reduce_hfr_fwd(const float* feat, const float* Wr, const flo
 
   ScaleArgs sa;
   sa.y = out; sa.part_sq = part_sq; sa.part_h = part_h; sa.W2 = W2; sa.b2 = b2; sa.scale = scale_out ? scale_out : scale;
+  sa.small = nullptr;
   sa.N = N; sa.C = C; sa.HW = HW; sa.tiles = tiles; sa.blocks = blocks;
   hfr_scale_kernel<<<N, 128, (size_t)C * 4, st>>>(sa);
   rc = launch_status("hfr_scale_kernel");
@@ -280,4 +608,220 @@ extern "C" int halo_reduce_hfr_fwd(const float* feat, const float* Wr, const flo
     hfr_apply_scalar_kernel<<<(int)b, 256, 0, st>>>(out, sa.scale, HW, total);
   }
   return launch_status("hfr_apply_kernel");
+}
+
+// ---- training mode ------------------------------------------------------------------------------------------------------
+namespace {
+struct TrainWs {
+  size_t part_sq, part_h, part_st, scale, bn, q, coef, v, part_bn, dbg, da, dy, gram, rsum, wrt, total;
+  int tiles, blocks, chunk, chunks;
+};
+TrainWs train_ws(int N, int Cin, int C, int H, int W) {
+  TrainWs L;
+  const size_t HW = (size_t)H * W;
+  L.tiles = (int)((HW + RH_TP - 1) / RH_TP);
+  L.blocks = (int)((HW + 127) / 128);
+  size_t chunk = (HW + 15) / 16;
+  if (chunk < 2048) chunk = 2048;
+  chunk = (chunk + 31) / 32 * 32;
+  L.chunk = (int)chunk;
+  L.chunks = (int)((HW + chunk - 1) / chunk);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += rh_align(bytes); return o; };
+  L.part_sq = take((size_t)N * L.tiles * C * 4);
+  L.part_h = take((size_t)N * L.blocks * C * 4);
+  L.part_st = take((size_t)N * L.blocks * 4 * 2 * C * 4);
+  L.scale = take((size_t)N * C * 4);
+  L.bn = take(2 * (size_t)C * 4);
+  L.q = take((size_t)N * C * 4);
+  L.coef = take((size_t)N * 2 * C * 4);
+  L.v = take((size_t)N * C * 4);
+  L.part_bn = take((size_t)N * L.blocks * 2 * C * 4);
+  L.dbg = take(2 * (size_t)C * 4);
+  L.da = take((size_t)N * C * HW * 4);
+  L.dy = take((size_t)N * C * HW * 4);
+  const size_t cmax = (size_t)(Cin > C ? Cin : C);
+  L.gram = take((size_t)N * L.chunks * C * cmax * 4);
+  L.rsum = take((size_t)N * L.chunks * C * 4);
+  L.wrt = take((size_t)Cin * C * 4);
+  L.total = off;
+  return L;
+}
+}  // namespace
+
+extern "C" size_t halo_reduce_hfr_train_workspace_bytes(int N, int Cin, int C, int H, int W) {
+  if (N <= 0 || Cin <= 0 || C <= 0 || H <= 0 || W <= 0) return 0;
+  return train_ws(N, Cin, C, H, W).total;
+}
+
+extern "C" int halo_reduce_hfr_train_fwd(const float* feat, const float* Wr, const float* br, const float* W1, const float* b1,
+                                         const float* bn_gamma, const float* bn_beta, float bn_eps, const float* W2,
+                                         const float* b2, const float* fixed_stats, float* y_out, float* z_out,
+                                         float* batch_stats, float* small, int N, int Cin, int C, int H, int W, void* ws,
+                                         size_t ws_bytes, halo_stream_t stream) {
+  HALO_CHECK_ARG(feat && Wr && y_out, "halo_reduce_hfr_train_fwd: NULL pointer");
+  HALO_CHECK_ARG(N > 0 && Cin > 0 && C > 0 && H > 0 && W > 0 && N <= 65535, "halo_reduce_hfr_train_fwd: bad dims");
+  const bool hfr = (W1 != nullptr);
+  HALO_CHECK_ARG(!hfr || (b1 && bn_gamma && bn_beta && W2 && b2 && z_out && batch_stats && small),
+                 "halo_reduce_hfr_train_fwd: the re-weighting MLP needs W1, b1, gamma, beta, W2, b2 and the z / statistics outputs");
+  if (hfr && C > 64) {
+    set_error("halo_reduce_hfr_train_fwd: training-mode HFR with %d reduced channels not compiled (<= 64)", C);
+    return HALO_ERR_UNSUPPORTED;
+  }
+  const TrainWs L = train_ws(N, Cin, C, H, W);
+  if (!ws || ws_bytes < L.total) {
+    set_error("halo_reduce_hfr_train_fwd: workspace %zu < %zu bytes", ws_bytes, L.total);
+    return HALO_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W;
+  unsigned char* w8 = (unsigned char*)ws;
+  float* part_sq = (float*)(w8 + L.part_sq);
+  float* part_h = (float*)(w8 + L.part_h);
+  float* part_st = (float*)(w8 + L.part_st);
+  float* scale = (float*)(w8 + L.scale);
+  float* bn = (float*)(w8 + L.bn);
+
+  ReduceArgs ra;
+  ra.f = feat; ra.Wr = Wr; ra.br = br; ra.y = y_out; ra.part_sq = hfr ? part_sq : nullptr;
+  ra.N = N; ra.Cin = Cin; ra.C = C; ra.HW = HW; ra.tiles = L.tiles;
+  reduce_kernel<<<dim3(L.tiles, (C + RH_TC - 1) / RH_TC, N), RH_THREADS, 0, st>>>(ra);
+  int rc = launch_status("reduce_kernel");
+  if (rc || !hfr) return rc;
+
+  HiddenArgs ha;
+  ha.y = y_out; ha.W1 = W1; ha.b1 = b1; ha.bn_scale = bn; ha.bn_shift = bn + C; ha.part_h = part_h;
+  ha.N = N; ha.C = C; ha.HW = HW; ha.blocks = L.blocks;
+  const size_t smem = ((size_t)C * C + 4 * C) * 4;
+  if (fixed_stats != nullptr) {   // BatchNorm1d in evaluation mode inside a differentiated step: its running statistics
+    HALO_CUDA(cudaMemcpyAsync(batch_stats, fixed_stats, 2 * (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+    bn_fold_kernel<<<1, 128, 0, st>>>(bn_gamma, bn_beta, fixed_stats, fixed_stats + C, bn_eps, bn, C);
+    rc = launch_status("bn_fold_kernel");
+    if (rc) return rc;
+  } else {
+    hidden_stats_kernel<64><<<dim3(L.blocks, N), 128, (size_t)C * C * 4, st>>>(ha, part_st);
+    rc = launch_status("hidden_stats_kernel");
+    if (rc) return rc;
+    hidden_stats_finish_kernel<<<1, 64, 0, st>>>(part_st, N * L.blocks * 4, HW, L.blocks, C, bn_gamma, bn_beta, bn_eps, bn, batch_stats);
+    rc = launch_status("hidden_stats_finish_kernel");
+    if (rc) return rc;
+  }
+  hidden_kernel<64><<<dim3(L.blocks, N), 128, smem, st>>>(ha);
+  rc = launch_status("hidden_kernel");
+  if (rc) return rc;
+
+  ScaleArgs sa;
+  sa.y = y_out; sa.part_sq = part_sq; sa.part_h = part_h; sa.W2 = W2; sa.b2 = b2; sa.scale = scale; sa.small = small;
+  sa.N = N; sa.C = C; sa.HW = HW; sa.tiles = L.tiles; sa.blocks = L.blocks;
+  hfr_scale_kernel<<<N, 128, (size_t)C * 4, st>>>(sa);
+  rc = launch_status("hfr_scale_kernel");
+  if (rc) return rc;
+  const long long total = (long long)N * C * HW;
+  long long b = (total + 255) / 256;
+  if (b > (long long)sm_count() * 16) b = (long long)sm_count() * 16;
+  hfr_apply_oop_kernel<<<(int)b, 256, 0, st>>>(y_out, scale, z_out, HW, total);
+  return launch_status("hfr_apply_oop_kernel");
+}
+
+extern "C" int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, const float* W1, const float* b1,
+                                         const float* bn_gamma, const float* bn_beta, float bn_eps, const float* W2,
+                                         const float* y, const float* batch_stats, const float* small, const float* dz,
+                                         float* dfeat, float* dWr, float* dbr, float* dW1, float* db1, float* dgamma,
+                                         float* dbeta, float* dW2, float* db2, int stats_are_batch, int N, int Cin, int C, int H,
+                                         int W, void* ws, size_t ws_bytes, halo_stream_t stream) {
+  HALO_CHECK_ARG(feat && Wr && dz && dWr, "halo_reduce_hfr_train_bwd: NULL pointer");
+  HALO_CHECK_ARG(N > 0 && Cin > 0 && C > 0 && H > 0 && W > 0 && N <= 65535, "halo_reduce_hfr_train_bwd: bad dims");
+  const bool hfr = (W1 != nullptr);
+  HALO_CHECK_ARG(!hfr || (b1 && bn_gamma && bn_beta && W2 && y && batch_stats && small && dW1 && db1 && dgamma && dbeta && dW2 && db2),
+                 "halo_reduce_hfr_train_bwd: the re-weighting MLP needs its parameters, the saved y / statistics and all gradient outputs");
+  if (hfr && C > 64) {
+    set_error("halo_reduce_hfr_train_bwd: training-mode HFR with %d reduced channels not compiled (<= 64)", C);
+    return HALO_ERR_UNSUPPORTED;
+  }
+  const TrainWs L = train_ws(N, Cin, C, H, W);
+  if (!ws || ws_bytes < L.total) {
+    set_error("halo_reduce_hfr_train_bwd: workspace %zu < %zu bytes", ws_bytes, L.total);
+    return HALO_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HW = H * W;
+  unsigned char* w8 = (unsigned char*)ws;
+  float* bn = (float*)(w8 + L.bn);
+  float* q = (float*)(w8 + L.q);
+  float* coef = (float*)(w8 + L.coef);
+  float* v = (float*)(w8 + L.v);
+  float* part_bn = (float*)(w8 + L.part_bn);
+  float* dbg = (float*)(w8 + L.dbg);
+  float* da = (float*)(w8 + L.da);
+  float* dyb = (float*)(w8 + L.dy);
+  float* gram = (float*)(w8 + L.gram);
+  float* rsum = (float*)(w8 + L.rsum);
+  float* wrt = (float*)(w8 + L.wrt);
+  int rc;
+  const float* dy = dz;   // without the re-weighting the reduced features ARE the output
+  if (hfr) {
+    dot_planes_kernel<<<N * C, 256, 0, st>>>(dz, y, q, HW);
+    rc = launch_status("dot_planes_kernel");
+    if (rc) return rc;
+    HfrSmallArgs sa;
+    sa.q = q; sa.small = small; sa.W2 = W2; sa.coef = coef; sa.v = v; sa.dW2 = dW2; sa.db2 = db2; sa.N = N; sa.C = C; sa.HW = HW;
+    const size_t sm_small = (size_t)N * C * 4;
+    HALO_CHECK_ARG(sm_small <= 200 * 1024, "halo_reduce_hfr_train_bwd: batch too large for the per-image scalar kernel");
+    HALO_CUDA(cudaFuncSetAttribute(hfr_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_small));
+    hfr_bwd_small_kernel<<<1, 256, sm_small, st>>>(sa);
+    rc = launch_status("hfr_bwd_small_kernel");
+    if (rc) return rc;
+    bn_fold_kernel<<<1, 128, 0, st>>>(bn_gamma, bn_beta, batch_stats, batch_stats + C, bn_eps, bn, C);
+    rc = launch_status("bn_fold_kernel");
+    if (rc) return rc;
+    HfrBnArgs ba;
+    ba.y = y; ba.W1 = W1; ba.b1 = b1; ba.bn = bn; ba.stats = batch_stats; ba.v = v; ba.eps = bn_eps; ba.part = part_bn;
+    ba.N = N; ba.C = C; ba.HW = HW; ba.blocks = L.blocks;
+    hfr_bwd_bn_sums_kernel<64><<<dim3(L.blocks, N), 128, ((size_t)C * C + 8 * C) * 4, st>>>(ba);
+    rc = launch_status("hfr_bwd_bn_sums_kernel");
+    if (rc) return rc;
+    sum_partials_kernel<<<1, 128, 0, st>>>(part_bn, N * L.blocks, 2 * C, dbg);
+    rc = launch_status("sum_partials_kernel");
+    if (rc) return rc;
+    HALO_CUDA(cudaMemcpyAsync(dbeta, dbg, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+    HALO_CUDA(cudaMemcpyAsync(dgamma, dbg + C, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+    HfrDaArgs da_a;
+    da_a.y = y; da_a.dz = dz; da_a.W1 = W1; da_a.b1 = b1; da_a.bn = bn; da_a.stats = batch_stats; da_a.v = v; da_a.dbg = dbg;
+    da_a.coef = coef; da_a.eps = bn_eps; da_a.da = da; da_a.dy = dyb; da_a.N = N; da_a.C = C; da_a.HW = HW;
+    // statistics that do not depend on the batch (evaluation-mode BatchNorm): the two correction terms vanish
+    da_a.inv_m = stats_are_batch ? (float)(1.0 / ((double)N * HW)) : 0.f;
+    hfr_bwd_da_kernel<64><<<dim3(L.blocks, N), 128, (size_t)C * C * 4, st>>>(da_a);
+    rc = launch_status("hfr_bwd_da_kernel");
+    if (rc) return rc;
+    dy = dyb;
+    // dW1 = sum da (x) y, db1 = sum da
+    GramArgs g1;
+    g1.A = da; g1.B = y; g1.part = gram; g1.rsum = rsum; g1.Ca = C; g1.Cb = C; g1.HW = HW; g1.chunk = L.chunk; g1.chunks = L.chunks;
+    gram_px_kernel<<<dim3((C + 63) / 64, (C + 63) / 64, N * L.chunks), 256, 0, st>>>(g1);
+    rc = launch_status("gram_px_kernel");
+    if (rc) return rc;
+    sum_partials_kernel<<<(C * C + 127) / 128, 128, 0, st>>>(gram, N * L.chunks, C * C, dW1);
+    sum_partials_kernel<<<1, 128, 0, st>>>(rsum, N * L.chunks, C, db1);
+    rc = launch_status("sum_partials_kernel");
+    if (rc) return rc;
+  }
+  // dWr = sum dy (x) f, dbr = sum dy
+  GramArgs g2;
+  g2.A = dy; g2.B = feat; g2.part = gram; g2.rsum = rsum; g2.Ca = C; g2.Cb = Cin; g2.HW = HW; g2.chunk = L.chunk; g2.chunks = L.chunks;
+  gram_px_kernel<<<dim3((Cin + 63) / 64, (C + 63) / 64, N * L.chunks), 256, 0, st>>>(g2);
+  rc = launch_status("gram_px_kernel");
+  if (rc) return rc;
+  sum_partials_kernel<<<(C * Cin + 127) / 128, 128, 0, st>>>(gram, N * L.chunks, C * Cin, dWr);
+  if (dbr != nullptr) sum_partials_kernel<<<1, 128, 0, st>>>(rsum, N * L.chunks, C, dbr);
+  rc = launch_status("sum_partials_kernel");
+  if (rc) return rc;
+  if (dfeat != nullptr) {   // df = Wr^T dy: the same register-tile kernel as the forward, with the transposed weight
+    transpose_kernel<<<(C * Cin + 255) / 256, 256, 0, st>>>(Wr, wrt, C, Cin);
+    ReduceArgs ra;
+    ra.f = dy; ra.Wr = wrt; ra.br = nullptr; ra.y = dfeat; ra.part_sq = nullptr;
+    ra.N = N; ra.Cin = C; ra.C = Cin; ra.HW = HW; ra.tiles = L.tiles;
+    reduce_kernel<<<dim3(L.tiles, (Cin + RH_TC - 1) / RH_TC, N), RH_THREADS, 0, st>>>(ra);
+    rc = launch_status("reduce_kernel (dfeat)");
+  }
+  return rc;
 }

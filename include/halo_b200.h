@@ -220,12 +220,34 @@ int halo_round_delta_apply(uint8_t* masks, const int* row_image, const int* pick
  *   feat [N,Cin,H,W] f32; Wr [C,Cin], br [C]|NULL (conv_reduce.weight / .bias);
  *   W1 [C,C], b1 [C], bn_gamma/beta/mean/var [C], bn_eps, W2 [C,C], b2 [C] (wn_mlp[0], [1], [3]); W1 = NULL: no HFR (z = y)
  *   out [N,C,H,W] f32 = z, the features HyperMapper.expmap / halo_head_fwd read next; scale_out [N,C] f32 | NULL = z / y
- * HFR needs C <= 128.  Forward only: a classifier in training mode (batch statistics, autograd) keeps its torch modules. */
+ * HFR needs C <= 128.  Evaluation-mode forward; the training mode is halo_reduce_hfr_train_fwd / _bwd below. */
 size_t halo_reduce_hfr_workspace_bytes(int N, int C, int H, int W);
 int halo_reduce_hfr_fwd(const float* feat, const float* Wr, const float* br, const float* W1, const float* b1,
                         const float* bn_gamma, const float* bn_beta, const float* bn_mean, const float* bn_var,
                         float bn_eps, const float* W2, const float* b2, float* out, float* scale_out,
                         int N, int Cin, int C, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
+
+/* Training mode of the same block (the training step's side of classifier.py:526-550): BatchNorm1d normalises with the
+ * statistics of the batch (all N*H*W rows), and halo_reduce_hfr_train_bwd is the autograd of the whole block.
+ *   fwd: y_out [N,C,H,W] = conv_reduce(f) (kept for the backward); z_out [N,C,H,W] = the re-weighted features (W1 = NULL:
+ *        no HFR, z = y, z_out unused); batch_stats [2][C] = batch mean and biased variance of the hidden pre-activations
+ *        (the caller updates running_mean / running_var from them, the variance times M/(M-1), M = N*H*W);
+ *        small [N][3][C] = per-image {mean hidden activation, re-weighting before the clamp, |y_c|} for the backward.
+ *   bwd: dz [N,C,H,W] -> dfeat [N,Cin,H,W] | NULL, dWr [C,Cin], dbr [C] | NULL, and with HFR dW1 [C,C], db1, dgamma, dbeta,
+ *        dW2 [C,C], db2 (all overwritten).  Fixed-order reductions: bitwise reproducible.
+ *   fixed_stats [2][C] | NULL: a BatchNorm1d left in evaluation mode inside a differentiated step normalises with its
+ *        running mean / variance; pass them here (they are copied to batch_stats) and stats_are_batch = 0 to the backward.
+ * Training-mode HFR needs C <= 64 (the channel count of every shipped HALO config); one workspace size serves both calls. */
+size_t halo_reduce_hfr_train_workspace_bytes(int N, int Cin, int C, int H, int W);
+int halo_reduce_hfr_train_fwd(const float* feat, const float* Wr, const float* br, const float* W1, const float* b1,
+                              const float* bn_gamma, const float* bn_beta, float bn_eps, const float* W2, const float* b2,
+                              const float* fixed_stats, float* y_out, float* z_out, float* batch_stats, float* small, int N,
+                              int Cin, int C, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
+int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, const float* W1, const float* b1, const float* bn_gamma,
+                              const float* bn_beta, float bn_eps, const float* W2, const float* y, const float* batch_stats,
+                              const float* small, const float* dz, float* dfeat, float* dWr, float* dbr, float* dW1,
+                              float* db1, float* dgamma, float* dbeta, float* dW2, float* db2, int stats_are_batch, int N,
+                              int Cin, int C, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
 
 /* ---- losses on the head's logits, fused with the up-sampling in front of them and its adjoint -------
  * Replaces, in the training step (core/train_learners.py:343-356 target branch, :232-236 source branch):

@@ -34,7 +34,7 @@ def test_reduce_hfr_matches_reference_block(shape):
     assert torch.equal(out, again)            # fixed-order reductions
 
 
-def test_reduce_hfr_feeds_the_fused_head_and_refuses_training_mode():
+def test_reduce_hfr_feeds_the_fused_head():
     N, Cin, C, O, H, W = 2, 512, 64, 19, 16, 32
     conv_reduce, wn_mlp = ohfr.build_modules(Cin, C, hfr=True, seed=3)
     conv_reduce.eval(); wn_mlp.eval()
@@ -47,12 +47,109 @@ def test_reduce_hfr_feeds_the_fused_head_and_refuses_training_mode():
         res = halo_b200.head_forward(z, P.to(DEV), A.to(DEV), 1.0, want_logits=True, want_radius=True)
     assert rel_err(res["logits"], logits_ref) <= 2 * TOL     # two fp32 stages chained against one fp64 chain
     assert rel_err(res["radius"], rad_ref) <= 2 * TOL
-    wn_mlp.train()
-    with pytest.raises(NotImplementedError):
-        reduce_hfr(f.to(DEV), conv_reduce, wn_mlp)
     with pytest.raises(RuntimeError, match="no CPU path"):
-        wn_mlp.eval()
         reduce_hfr(f, conv_reduce, wn_mlp)
+
+
+def _train_reference(f, conv_reduce, wn_mlp, dz, bn_train=True):
+    """The reference block (oracle/hfr.py = classifier.py:526-550) in float64 with torch autograd: output, every gradient, and
+    the BatchNorm running statistics after the step."""
+    conv, mlp = copy.deepcopy(conv_reduce).double(), (copy.deepcopy(wn_mlp).double() if wn_mlp is not None else None)
+    conv.train()
+    if mlp is not None:
+        mlp.train(bn_train)
+    x = f.double().clone().requires_grad_(True)
+    z = ohfr.reduce_hfr(x, conv, mlp)
+    (z * dz.double()).sum().backward()
+    grads = {"x": x.grad}
+    for name, p in list(conv.named_parameters()) + ([("mlp." + k, v) for k, v in mlp.named_parameters()] if mlp is not None else []):
+        grads[name] = p.grad
+    return z.detach(), grads, mlp
+
+
+@pytest.mark.parametrize("shape", [(2, 512, 64, 20, 40, True, True), (3, 96, 32, 9, 13, True, True), (1, 304, 64, 33, 65, True, True),
+                                   (2, 512, 64, 20, 40, True, False), (2, 512, 64, 20, 40, False, True), (1, 70, 19, 5, 7, False, True),
+                                   (2, 256, 48, 16, 16, True, True)])
+def test_reduce_hfr_training_mode_forward_backward(shape):
+    """Training step: BatchNorm1d on batch statistics (or left in eval mode: bn_train False), gradients to the features and to
+    every parameter of conv_reduce / wn_mlp, running statistics updated like torch -- against float64 autograd through the
+    reference block."""
+    N, Cin, C, H, W, hfr, bn_train = shape
+    conv_reduce, wn_mlp = ohfr.build_modules(Cin, C, hfr=hfr, seed=Cin + C + 1)
+    f = torch.randn((N, Cin, H, W), generator=torch.Generator().manual_seed(5))
+    dz = torch.randn((N, C, H, W), generator=torch.Generator().manual_seed(6))
+    z_ref, g_ref, mlp_ref = _train_reference(f, conv_reduce, wn_mlp, dz, bn_train)
+
+    conv, mlp = copy.deepcopy(conv_reduce).to(DEV), (copy.deepcopy(wn_mlp).to(DEV) if hfr else None)
+    conv.train()
+    if hfr:
+        mlp.train(bn_train)
+    x = f.to(DEV).requires_grad_(True)
+    z = reduce_hfr(x, conv, mlp)
+    assert z.requires_grad and tuple(z.shape) == (N, C, H, W)
+    assert rel_err(z, z_ref) <= TOL
+    (z * dz.to(DEV)).sum().backward()
+    assert rel_err(x.grad, g_ref["x"]) <= 1e-4
+    got = dict(list(conv.named_parameters()) + ([("mlp." + k, v) for k, v in mlp.named_parameters()] if hfr else []))
+    # the bias in front of a batch-statistics BatchNorm has an exactly zero gradient (1e-16 in float64): measure every
+    # parameter gradient against the larger of its own magnitude and 1e-2 of the largest parameter gradient (the zero comes
+    # out of a cancelling fp32 sum over all pixels)
+    floor = 1e-2 * max(float(v.abs().max()) for k, v in g_ref.items() if k != "x")
+    for name, ref in g_ref.items():
+        if name == "x":
+            continue
+        assert got[name].grad is not None, name
+        err = float((got[name].grad.detach().cpu().double() - ref).abs().max()) / max(float(ref.abs().max()), floor)
+        assert err <= 1e-4, (name, err)
+    if hfr:
+        bn, bn_ref = mlp[1], mlp_ref[1]
+        assert rel_err(bn.running_mean, bn_ref.running_mean) <= TOL and rel_err(bn.running_var, bn_ref.running_var) <= TOL
+        assert int(bn.num_batches_tracked) == int(bn_ref.num_batches_tracked)
+    # fixed-order reductions: a second step from the same state returns the same bits
+    conv2, mlp2 = copy.deepcopy(conv_reduce).to(DEV), (copy.deepcopy(wn_mlp).to(DEV) if hfr else None)
+    conv2.train()
+    if hfr:
+        mlp2.train(bn_train)
+    x2 = f.to(DEV).requires_grad_(True)
+    z2 = reduce_hfr(x2, conv2, mlp2)
+    (z2 * dz.to(DEV)).sum().backward()
+    assert torch.equal(z, z2) and torch.equal(x.grad, x2.grad) and torch.equal(conv.weight.grad, conv2.weight.grad)
+
+
+def test_reduce_hfr_training_mode_chains_into_the_fused_head_and_loss():
+    """conv_reduce + HFR -> fused head -> fused loss, one autograd graph, against the same chain in float64 torch."""
+    from halo_b200.losses import fused_seg_loss
+    from oracle import loss as oloss
+
+    N, Cin, C, O, H, W = 2, 128, 64, 19, 12, 20
+    conv_reduce, wn_mlp = ohfr.build_modules(Cin, C, hfr=True, seed=11)
+    P, A = halo_b200.synth.head_params(O, C, seed=4, dtype=torch.float64)
+    f = torch.randn((N, Cin, H, W), generator=torch.Generator().manual_seed(7)) * 0.3
+    labels = torch.randint(0, O, (N, 4 * H, 4 * W), generator=torch.Generator().manual_seed(8))
+    labels[:, ::3] = 255
+    # reference chain
+    conv, mlp = copy.deepcopy(conv_reduce).double().train(), copy.deepcopy(wn_mlp).double().train()
+    Pr, Ar = P.clone().requires_grad_(True), A.clone().requires_grad_(True)
+    z = ohfr.reduce_hfr(f.double(), conv, mlp)
+    logits = ohead.mlr_logits(ohead.expmap(z, 1.0, dim=1).double(), Pr, Ar, 1.0)
+    up = torch.nn.functional.interpolate(logits, size=(4 * H, 4 * W), mode="bilinear", align_corners=True)
+    loss_ref = torch.nn.functional.cross_entropy(up, labels.long(), ignore_index=255) + \
+        oloss.negative_learning_loss(torch.softmax(up, dim=1), 0.05)
+    loss_ref.backward()
+    # fused chain
+    convd, mlpd = copy.deepcopy(conv_reduce).to(DEV).train(), copy.deepcopy(wn_mlp).to(DEV).train()
+    head = halo_b200.HyperMLR(C, O, c=1.0).to(DEV)
+    with torch.no_grad():
+        head.P_MLR.copy_(P); head.A_MLR.copy_(A)
+    mapper = halo_b200.HyperMapper(c=1.0)
+    zz = reduce_hfr(f.to(DEV), convd, mlpd)
+    out = head(mapper.expmap(zz, dim=1))
+    loss = fused_seg_loss(out, labels.to(DEV), (4 * H, 4 * W), 1.0, 0.05)[0]
+    loss.backward()
+    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert rel_err(convd.weight.grad, conv.weight.grad) <= 2e-4
+    assert rel_err(mlpd[0].weight.grad, mlp[0].weight.grad) <= 2e-4
+    assert rel_err(head.P_MLR.grad, Pr.grad) <= 2e-4
 
 
 def test_reference_classifier_golden(golden):

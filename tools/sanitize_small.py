@@ -45,5 +45,8 @@ conv = torch.nn.Conv2d(96, 32, 1).to(dev).eval()
 mlp = torch.nn.Sequential(torch.nn.Linear(32, 32), torch.nn.BatchNorm1d(32), torch.nn.ReLU(), torch.nn.Linear(32, 32)).to(dev).eval()
 with torch.no_grad():
     z = reduce_hfr(torch.randn(2, 96, 9, 11, device=dev), conv, mlp)
+conv.train(); mlp.train()
+zt = reduce_hfr(torch.randn(2, 96, 9, 11, device=dev, requires_grad=True), conv, mlp)    # training mode: batch statistics + backward
+zt.square().sum().backward()
 torch.cuda.synchronize()
 print("ok", dus, float(dP.abs().max()), int(res["n_picked"].min()), float(x.grad.abs().max()), float(z.abs().max()))
