@@ -612,6 +612,7 @@ def run_train_step(feat8, P, A, c, peak):
     P64, A64 = synth.head_params(P.shape[0], 64, seed=0, device=feat8.device)
     out["c64"] = measure(feat8[:2].reshape(B, 64, H, W), P64, A64)   # the same bytes viewed as 8 images of 64 channels
     out["fused_loss"] = run_loss_step(feat8.device, P.shape[0])
+    out["head_block"] = run_head_block_step(feat8.device, P.shape[0])
     return out
 
 
@@ -662,6 +663,86 @@ def run_loss_step(dev, O):
     res["loss_rel_diff"] = abs(float(a[0]) - float(b[0])) / abs(float(b[0]))
     res["grad_rel_diff_of_max"] = float((a[1] - b[1]).abs().max() / b[1].abs().max())
     res["workload"] = "fwd+bwd of CE(ignore 255) + negative-learning loss on logits %dx%dx%dx%d up-sampled to %dx%d" % (N, O, h, w, H, W)
+    return res
+
+
+def run_head_block_step(dev, O):
+    """SURVEY 8f rows 3 + 4 around the head at the reference's training shape (batch 4, decoder features 512 x 160x320,
+    REDUCED_CHANNELS 64, labels 640x1280): conv_reduce + HFR in training mode -> fused head -> fused loss, forward AND
+    backward to the decoder features and every parameter, as ONE autograd graph of this library's kernels.  Beside it the
+    conv_reduce + HFR part alone against the reference's torch call sequence (classifier.py:527-550) run eagerly on the
+    same GPU with the same modules."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+
+    import halo_b200
+    from halo_b200.hfr import reduce_hfr
+    from halo_b200.losses import fused_seg_loss
+
+    N, Cin, C, h, w, H, W = 4, 512, 64, 160, 320, 640, 1280
+    torch.manual_seed(5)
+    conv = nn.Conv2d(Cin, C, 1).to(dev).train()
+    mlp = nn.Sequential(nn.Linear(C, C), nn.BatchNorm1d(C), nn.ReLU(), nn.Linear(C, C)).to(dev).train()
+    head = halo_b200.HyperMLR(C, O, c=1.0).to(dev)
+    mapper = halo_b200.HyperMapper(c=1.0)
+    g = torch.Generator(device=dev).manual_seed(12)
+    feats = torch.randn((N, Cin, h, w), device=dev, generator=g) * 0.3
+    labels = torch.randint(0, O, (N, H, W), device=dev, generator=g)
+    labels[torch.rand((N, H, W), device=dev, generator=g) > 0.05] = 255
+    lab8 = labels.to(torch.uint8)
+    params = list(conv.parameters()) + list(mlp.parameters()) + list(head.parameters())
+
+    def zero():
+        for p in params:
+            p.grad = None
+
+    def block():
+        zero()
+        x = feats.detach().requires_grad_(True)
+        z = reduce_hfr(x, conv, mlp)
+        out = head(mapper.expmap(z, dim=1))
+        loss, _, _ = fused_seg_loss(out, lab8, (H, W), 1.0)
+        loss.backward()
+        return x.grad
+
+    def hfr_ours():
+        zero()
+        x = feats.detach().requires_grad_(True)
+        z = reduce_hfr(x, conv, mlp)
+        z.backward(dz)
+        return z, x.grad, conv.weight.grad
+
+    def hfr_torch():
+        zero()
+        x = feats.detach().requires_grad_(True)
+        y = conv(x)
+        t = mlp(y.permute(0, 2, 3, 1).contiguous().view(-1, C)).view(-1, h * w, C)
+        wt = torch.clamp(torch.mean(t, dim=1).view(-1, C, 1, 1), min=1e-5)
+        z = F.normalize(y.reshape(-1, C, h * w), dim=-1).reshape(-1, C, h, w) * wt
+        z.backward(dz)
+        return z, x.grad, conv.weight.grad
+
+    dz = torch.randn((N, C, h, w), device=dev, generator=g)
+    res, vals = {}, {}
+    tf32_was = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False     # the torch arm in fp32 like this library (cuDNN's default would run the conv in TF32)
+    for name, fn in (("head_block_fwd_bwd", block), ("reduce_hfr_train", hfr_ours), ("reduce_hfr_torch_eager", hfr_torch)):
+        for _ in range(2):
+            vals[name] = fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name + "_ms"] = round(e0.elapsed_time(e1) / 5, 3)
+    torch.backends.cudnn.allow_tf32 = tf32_was
+    a, b = vals["reduce_hfr_train"], vals["reduce_hfr_torch_eager"]
+    res["z_rel_diff_of_max"] = float((a[0] - b[0]).abs().max() / b[0].abs().max())
+    res["dfeat_rel_diff_of_max"] = float((a[1] - b[1]).abs().max() / b[1].abs().max())
+    res["dWr_rel_diff_of_max"] = float((a[2] - b[2]).abs().max() / b[2].abs().max())
+    res["workload"] = ("training step of the head block: conv_reduce %d->%d + HFR (BatchNorm on batch statistics), fused head, "
+                       "fused loss; batch %d, decoder features %dx%d, labels %dx%d, %d classes" % (Cin, C, N, h, w, H, W, O))
     return res
 
 

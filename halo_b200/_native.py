@@ -61,8 +61,8 @@ _SIGNATURES = {
     "halo_checksum64": (_i, [_vp, _sz, ctypes.c_ulonglong, _vp, _i, _vp]),
     "halo_reduce_hfr_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "halo_reduce_hfr_train_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
-    "halo_reduce_hfr_train_fwd": (_i, [_vp] * 7 + [_f] + [_vp] * 7 + [_i] * 5 + [_vp, _sz, _vp]),
-    "halo_reduce_hfr_train_bwd": (_i, [_vp] * 6 + [_f] + [_vp] * 14 + [_i] * 6 + [_vp, _sz, _vp]),
+    "halo_reduce_hfr_train_fwd": (_i, [_vp] * 7 + [_f] + [_vp] * 8 + [_i] * 5 + [_vp, _sz, _vp]),
+    "halo_reduce_hfr_train_bwd": (_i, [_vp] * 5 + [_f] + [_vp] * 15 + [_i] * 6 + [_vp, _sz, _vp]),
     "halo_reduce_hfr_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _sz, _vp]),
     "halo_seg_loss_workspace_bytes": (_sz, []),
     "halo_seg_loss": (_i, [_vp, _vp, _f, _f, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp]),

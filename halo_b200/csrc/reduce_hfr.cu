@@ -17,30 +17,32 @@
 
 namespace halo {
 
-constexpr int RH_TP = 64;        // pixels per tile
+constexpr int RH_TP = 128;       // pixels per tile
 constexpr int RH_TC = 64;        // output channels per tile
 constexpr int RH_TK = 32;        // input channels per shared-memory stage
-constexpr int RH_THREADS = 256;  // 16 x 16 threads, 4 px x 4 ch each
+constexpr int RH_THREADS = 256;  // 16 x 16 threads, 8 px x 4 ch each
 
 struct ReduceArgs {
   const float* f;     // [N,Cin,HW]
   const float* Wr;    // [C,Cin]
   const float* br;    // [C] | NULL
   float* y;           // [N,C,HW]
-  float* part_sq;     // [N][tiles][C]  partial sums of y^2
+  float* part_sq;     // [N][tiles][C]  partial sums of y^2 | NULL
   int N, Cin, C, HW, tiles;
 };
 
+// y[c][p] = sum_k W[c][k] f[k][p] + b[c].  A thread owns pixels {4 tx .. 4 tx + 3} and {64 + 4 tx ..} of the tile and channels
+// {4 ty ..}: per input channel two conflict-free LDS.128 of features and one broadcast LDS.128 of weights feed 32 FMAs.
 __global__ void __launch_bounds__(RH_THREADS) reduce_kernel(const ReduceArgs a) {
-  __shared__ float sF[RH_TK][RH_TP];        // [k][px]
-  __shared__ float sW[RH_TK][RH_TC + 1];    // [k][ch]
+  __shared__ __align__(16) float sF[RH_TK][RH_TP];   // [k][px]
+  __shared__ __align__(16) float sW[RH_TK][RH_TC];   // [k][ch]
   __shared__ float sSq[16][RH_TC];
   const int tile = blockIdx.x, n = blockIdx.z, cb = blockIdx.y * RH_TC;
   const int p0 = tile * RH_TP;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx: pixel quad, ty: channel quad
-  float acc[4][4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // tx: pixel quads, ty: channel quad
+  float acc[8][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const float* fn = a.f + (size_t)n * a.Cin * a.HW;
@@ -56,15 +58,16 @@ __global__ void __launch_bounds__(RH_THREADS) reduce_kernel(const ReduceArgs a) 
     __syncthreads();
 #pragma unroll 8
     for (int k = 0; k < RH_TK; ++k) {
-      const float4 fv = *reinterpret_cast<const float4*>(&sF[k][tx * 4]);
-      const float w0 = sW[k][ty * 4 + 0], w1 = sW[k][ty * 4 + 1], w2 = sW[k][ty * 4 + 2], w3 = sW[k][ty * 4 + 3];
-      const float fp[4] = {fv.x, fv.y, fv.z, fv.w};
+      const float4 f0 = *reinterpret_cast<const float4*>(&sF[k][tx * 4]);
+      const float4 f1 = *reinterpret_cast<const float4*>(&sF[k][64 + tx * 4]);
+      const float4 wv = *reinterpret_cast<const float4*>(&sW[k][ty * 4]);
+      const float fp[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc[i][0] = fmaf(fp[i], w0, acc[i][0]);
-        acc[i][1] = fmaf(fp[i], w1, acc[i][1]);
-        acc[i][2] = fmaf(fp[i], w2, acc[i][2]);
-        acc[i][3] = fmaf(fp[i], w3, acc[i][3]);
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] = fmaf(fp[i], wv.x, acc[i][0]);
+        acc[i][1] = fmaf(fp[i], wv.y, acc[i][1]);
+        acc[i][2] = fmaf(fp[i], wv.z, acc[i][2]);
+        acc[i][3] = fmaf(fp[i], wv.w, acc[i][3]);
       }
     }
     __syncthreads();
@@ -75,17 +78,29 @@ __global__ void __launch_bounds__(RH_THREADS) reduce_kernel(const ReduceArgs a) 
     const int c = cb + ty * 4 + j;
     if (c >= a.C) continue;
     const float b = (a.br != nullptr) ? a.br[c] : 0.f;
-    float* yr = a.y + ((size_t)n * a.C + c) * a.HW + p0 + tx * 4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (p0 + tx * 4 + i < a.HW) {
-        const float v = acc[i][j] + b;
-        yr[i] = v;
-        sq[j] = fmaf(v, v, sq[j]);
+    for (int h = 0; h < 2; ++h) {
+      const int pp = p0 + h * 64 + tx * 4;
+      float* yr = a.y + ((size_t)n * a.C + c) * a.HW + pp;
+      float v[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = acc[h * 4 + i][j] + b;
+      if (pp + 3 < a.HW && (a.HW & 3) == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0) {
+        *reinterpret_cast<float4*>(yr) = make_float4(v[0], v[1], v[2], v[3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sq[j] = fmaf(v[i], v[i], sq[j]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (pp + i < a.HW) {
+            yr[i] = v[i];
+            sq[j] = fmaf(v[i], v[i], sq[j]);
+          }
+        }
       }
     }
   }
-  // per-channel sum of squares of this tile: fixed-order reduction over the 16 pixel quads
+  // per-channel sum of squares of this tile: fixed-order reduction over the 16 pixel groups
 #pragma unroll
   for (int j = 0; j < 4; ++j) sSq[tx][ty * 4 + j] = sq[j];
   __syncthreads();
@@ -203,7 +218,7 @@ __global__ void hfr_apply_scalar_kernel(float* __restrict__ y, const float* __re
 // =====================================================================================================================
 // Training mode (the training step's side of classifier.py:526-550): BatchNorm1d normalises with the
 // statistics of the batch (all N*h*w rows), and autograd runs back through the re-weighting, the normalisation and the
-// 1x1 convolution.  Forward = the kernels above with the batch statistics folded in, plus hidden_stats_kernel; backward:
+// 1x1 convolution.  Forward = the kernels above with the batch statistics folded in; backward:
 //   dwt[n,c] = <dz, y_hat> ; dy1 = wt/|y| (dz - y_hat dwt)                               (normalise * weight)
 //   dtbar = dwt [tbar >= 1e-5] ; dW2 = sum_n dtbar (x) hbar ; db2 = sum_n dtbar ; v[n,:] = W2^T dtbar[n] / HW  (mean, Linear 2)
 //   g = v [b > 0] ; dbeta = sum g ; dgamma = sum g x_hat ; da = gamma/sigma (g - dbeta/M - x_hat dgamma/M)   (ReLU, BatchNorm)
@@ -212,63 +227,111 @@ __global__ void hfr_apply_scalar_kernel(float* __restrict__ y, const float* __re
 // Every sum over pixels goes through per-block partials and a fixed-order finish: bitwise reproducible.
 // =====================================================================================================================
 
-// per warp of 32 pixels and hidden unit j: (sum, M2 about the warp mean) of a = W1 y + b1 -- combined with Chan's formula
-// in double by hidden_stats_finish_kernel (a one-pass E[a^2] - mean^2 in fp32 loses the variance when |mean| >> sigma)
-template <int CMAX>
-__global__ void __launch_bounds__(128) hidden_stats_kernel(const HiddenArgs a, float* __restrict__ part /* [N][blocks][4 warps][2][C] */) {
-  extern __shared__ float sm[];
-  float* sW1 = sm;   // [C][C]
-  const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < a.C * a.C; i += 128) sW1[i] = a.W1[i];
+// The hidden pre-activations a = W1 y + b1 are one more 1x1 convolution (reduce_kernel with Cin = C) kept as a plane tensor
+// [N][C][HW]; everything BatchNorm / ReLU needs in either direction is then a per-plane reduction or an element-wise pass.
+
+// fixed-order block sum of one value per thread (256 threads)
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  red[threadIdx.x] = v;
   __syncthreads();
-  const int p = blockIdx.x * 128 + threadIdx.x;
-  const bool live = p < a.HW;
-  float yv[CMAX];
-#pragma unroll
-  for (int c = 0; c < CMAX; ++c) yv[c] = (live && c < a.C) ? a.y[((size_t)n * a.C + c) * a.HW + p] : 0.f;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cnt = __popc(__ballot_sync(0xffffffffu, live));
-  float* o = part + (((size_t)n * a.blocks + blockIdx.x) * 4 + warp) * 2 * a.C;
-  for (int j = 0; j < a.C; ++j) {
-    const float* wr = sW1 + (size_t)j * a.C;
-    float t = a.b1[j];
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < a.C) t = fmaf(wr[c], yv[c], t);
-    float s = live ? t : 0.f;
-#pragma unroll
-    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
-    const float mean = cnt ? s / (float)cnt : 0.f;
-    float d = live ? (t - mean) : 0.f;
-    d *= d;
-#pragma unroll
-    for (int o2 = 16; o2 > 0; o2 >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o2);
-    if (lane == 0) { o[j] = s; o[a.C + j] = d; }
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
   }
+  const float r = red[0];
+  __syncthreads();
+  return r;
 }
 
-// one block: combine the warp partials in a fixed order (Chan et al.), fold the batch statistics into scale / shift
-__global__ void hidden_stats_finish_kernel(const float* __restrict__ part, int groups /* N*blocks*4 */, int HW, int blocks, int C,
-                                           const float* g, const float* b, float eps, float* bn /* [2][C] */, float* stats /* [2][C] */) {
-  for (int j = threadIdx.x; j < C; j += blockDim.x) {
-    double n_tot = 0.0, mean = 0.0, M2 = 0.0;
-    for (int q = 0; q < groups; ++q) {
-      const int blk = (q / 4) % blocks, w = q & 3;
-      int cnt = HW - (blk * 128 + w * 32);
-      cnt = cnt < 0 ? 0 : (cnt > 32 ? 32 : cnt);
-      if (cnt == 0) continue;
-      const double s = part[(size_t)q * 2 * C + j], m2 = part[(size_t)q * 2 * C + C + j];
-      const double mb = s / cnt, delta = mb - mean, nn = n_tot + cnt;
-      M2 += m2 + delta * delta * n_tot * cnt / nn;
-      mean += delta * cnt / nn;
-      n_tot = nn;
+// one block per (n, j) plane: sum and M2 about the plane's own mean (two passes over an L2-resident plane; a one-pass
+// E[a^2] - mean^2 in fp32 loses the variance when |mean| >> sigma)
+__global__ void __launch_bounds__(256) plane_stats_kernel(const float* __restrict__ a, float* __restrict__ part /* [planes][2] */, int HW) {
+  __shared__ float red[256];
+  const float* pl = a + (size_t)blockIdx.x * HW;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) s += pl[p];
+  const float sum = block_sum_256(s, red);
+  const float mean = sum / (float)HW;
+  float m2 = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    const float d = pl[p] - mean;
+    m2 = fmaf(d, d, m2);
+  }
+  m2 = block_sum_256(m2, red);
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = sum; part[2 * blockIdx.x + 1] = m2; }
+}
+
+// combine the N planes of every hidden unit in a fixed order (double), fold the batch statistics into scale / shift
+__global__ void plane_stats_finish_kernel(const float* __restrict__ part, int N, int HW, int C, const float* g, const float* b, float eps,
+                                          float* bn /* [2][C] */, float* stats /* [2][C] */) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < C; j += gridDim.x * blockDim.x) {
+    double S = 0.0;
+    for (int n = 0; n < N; ++n) S += part[2 * ((size_t)n * C + j)];
+    const double mean = S / ((double)N * HW);
+    double M2 = 0.0;
+    for (int n = 0; n < N; ++n) {
+      const double d = part[2 * ((size_t)n * C + j)] / (double)HW - mean;
+      M2 += part[2 * ((size_t)n * C + j) + 1] + d * d * HW;
     }
-    const double var = M2 / n_tot;   // biased, what BatchNorm normalises with
+    const double var = M2 / ((double)N * HW);   // biased, what BatchNorm normalises with
     const float sc = (float)((double)g[j] / sqrt(var + (double)eps));
     bn[j] = sc;
     bn[C + j] = (float)((double)b[j] - mean * (double)sc);
     stats[j] = (float)mean;
     stats[C + j] = (float)var;
+  }
+}
+
+// one block per (n, j) plane: sum over the pixels of relu(bn(a)) -> part_h[n][j]
+__global__ void __launch_bounds__(256) plane_hidden_sum_kernel(const float* __restrict__ a, const float* __restrict__ bn, float* __restrict__ out,
+                                                               int C, int HW) {
+  __shared__ float red[256];
+  const int j = blockIdx.x % C;
+  const float sc = bn[j], sh = bn[C + j];
+  const float* pl = a + (size_t)blockIdx.x * HW;
+  float s = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) s += fmaxf(fmaf(pl[p], sc, sh), 0.f);
+  s = block_sum_256(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// one block per (n, j) plane: sum g and sum g * x_hat with g = v[n][j] * [bn(a) > 0]  -> part[n][2][C]
+__global__ void __launch_bounds__(256) plane_bn_sums_kernel(const float* __restrict__ a, const float* __restrict__ bn, const float* __restrict__ stats,
+                                                            const float* __restrict__ v, float eps, float* __restrict__ part, int C, int HW) {
+  __shared__ float red[256];
+  const int n = blockIdx.x / C, j = blockIdx.x - n * C;
+  const float sc = bn[j], sh = bn[C + j], mean = stats[j], isd = rsqrtf(stats[C + j] + eps), vj = v[blockIdx.x];
+  const float* pl = a + (size_t)blockIdx.x * HW;
+  float g = 0.f, gx = 0.f;
+  for (int p = threadIdx.x; p < HW; p += 256) {
+    const float t = pl[p];
+    if (fmaf(t, sc, sh) > 0.f) { g += vj; gx = fmaf(vj, (t - mean) * isd, gx); }
+  }
+  g = block_sum_256(g, red);
+  gx = block_sum_256(gx, red);
+  if (threadIdx.x == 0) { part[((size_t)n * 2 + 0) * C + j] = g; part[((size_t)n * 2 + 1) * C + j] = gx; }
+}
+
+// element-wise: da = gamma/sigma (g - dbeta/M - x_hat dgamma/M)
+__global__ void hfr_da_elem_kernel(const float* __restrict__ a, const float* __restrict__ bn, const float* __restrict__ stats,
+                                   const float* __restrict__ v, const float* __restrict__ dbg, float eps, float inv_m,
+                                   float* __restrict__ da, int C, int HW, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long plane = i / HW;
+    const int j = (int)(plane % C);
+    const float t = a[i], sc = bn[j];
+    const float g = (fmaf(t, sc, bn[C + j]) > 0.f) ? v[plane] : 0.f;
+    const float xh = (t - stats[j]) * rsqrtf(stats[C + j] + eps);
+    da[i] = sc * (g - dbg[j] * inv_m - xh * dbg[C + j] * inv_m);
+  }
+}
+// element-wise: dy = dy2 + coef0 dz - coef1 y   (dy holds W1^T da on entry)
+__global__ void hfr_dy_finish_kernel(float* __restrict__ dy, const float* __restrict__ dz, const float* __restrict__ y,
+                                     const float* __restrict__ coef, int C, int HW, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long plane = i / HW;
+    const int n = (int)(plane / C), c = (int)(plane - (long long)n * C);
+    dy[i] = fmaf(coef[((size_t)n * 2 + 0) * C + c], dz[i], fmaf(-coef[((size_t)n * 2 + 1) * C + c], y[i], dy[i]));
   }
 }
 
@@ -339,55 +402,6 @@ __global__ void hfr_bwd_small_kernel(const HfrSmallArgs a) {
   }
 }
 
-struct HfrBnArgs {
-  const float* y;        // [N][C][HW]
-  const float* W1;       // [C][C]
-  const float* b1;       // [C]
-  const float* bn;       // [2][C] scale = gamma/sigma, shift = beta - mean*scale   (batch statistics)
-  const float* stats;    // [2][C] batch mean, biased variance
-  const float* v;        // [N][C]
-  float eps;
-  float* part;           // [N][blocks][2][C]  sum g, sum g*x_hat
-  int N, C, HW, blocks;
-};
-template <int CMAX>
-__global__ void __launch_bounds__(128) hfr_bwd_bn_sums_kernel(const HfrBnArgs a) {
-  extern __shared__ float sm[];
-  float* sW1 = sm;                          // [C][C]
-  float* sRed = sm + (size_t)a.C * a.C;     // [4 warps][2][C]
-  const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < a.C * a.C; i += 128) sW1[i] = a.W1[i];
-  __syncthreads();
-  const int p = blockIdx.x * 128 + threadIdx.x;
-  const bool live = p < a.HW;
-  float yv[CMAX];
-#pragma unroll
-  for (int c = 0; c < CMAX; ++c) yv[c] = (live && c < a.C) ? a.y[((size_t)n * a.C + c) * a.HW + p] : 0.f;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = 0; j < a.C; ++j) {
-    const float* wr = sW1 + (size_t)j * a.C;
-    float t = a.b1[j];
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < a.C) t = fmaf(wr[c], yv[c], t);
-    const float bval = fmaf(t, a.bn[j], a.bn[a.C + j]);
-    const float xh = (t - a.stats[j]) * rsqrtf(a.stats[a.C + j] + a.eps);
-    float g = (live && bval > 0.f) ? a.v[(size_t)n * a.C + j] : 0.f;
-    float gx = g * xh;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      g += __shfl_xor_sync(0xffffffffu, g, o);
-      gx += __shfl_xor_sync(0xffffffffu, gx, o);
-    }
-    if (lane == 0) { sRed[(warp * 2 + 0) * a.C + j] = g; sRed[(warp * 2 + 1) * a.C + j] = gx; }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * a.C; i += 128) {
-    float s = 0.f;
-    for (int w = 0; w < 4; ++w) s += sRed[(size_t)w * 2 * a.C + i];
-    a.part[((size_t)n * a.blocks + blockIdx.x) * 2 * a.C + i] = s;
-  }
-}
 // fixed-order finish of [groups][rows] partials in double: out[i] = sum_g part[g][i]
 __global__ void sum_partials_kernel(const float* __restrict__ part, int groups, int rows, float* __restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
@@ -397,65 +411,9 @@ __global__ void sum_partials_kernel(const float* __restrict__ part, int groups, 
   }
 }
 
-struct HfrDaArgs {
-  const float* y;        // [N][C][HW]
-  const float* dz;       // [N][C][HW]
-  const float* W1;
-  const float* b1;
-  const float* bn;       // [2][C]
-  const float* stats;    // [2][C]
-  const float* v;        // [N][C]
-  const float* dbg;      // [2][C] dbeta, dgamma
-  const float* coef;     // [N][2][C]
-  float eps;
-  float* da;             // [N][C][HW]
-  float* dy;             // [N][C][HW]
-  int N, C, HW;
-  float inv_m;           // 1 / (N*HW)
-};
-// thread = pixel: da (for dW1 / db1) and dy = dy1 + W1^T da
-template <int CMAX>
-__global__ void __launch_bounds__(128) hfr_bwd_da_kernel(const HfrDaArgs a) {
-  extern __shared__ float sm[];
-  float* sW1 = sm;   // [C][C]
-  const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < a.C * a.C; i += 128) sW1[i] = a.W1[i];
-  __syncthreads();
-  const int p = blockIdx.x * 128 + threadIdx.x;
-  if (p >= a.HW) return;
-  float yv[CMAX], dyv[CMAX];
-#pragma unroll
-  for (int c = 0; c < CMAX; ++c) {
-    yv[c] = (c < a.C) ? a.y[((size_t)n * a.C + c) * a.HW + p] : 0.f;
-    dyv[c] = 0.f;
-  }
-  for (int j = 0; j < a.C; ++j) {
-    const float* wr = sW1 + (size_t)j * a.C;
-    float t = a.b1[j];
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < a.C) t = fmaf(wr[c], yv[c], t);
-    const float bval = fmaf(t, a.bn[j], a.bn[a.C + j]);
-    const float xh = (t - a.stats[j]) * rsqrtf(a.stats[a.C + j] + a.eps);
-    const float g = (bval > 0.f) ? a.v[(size_t)n * a.C + j] : 0.f;
-    const float d = a.bn[j] * (g - a.dbg[j] * a.inv_m - xh * a.dbg[a.C + j] * a.inv_m);   // bn[j] = gamma / sigma
-    a.da[((size_t)n * a.C + j) * a.HW + p] = d;
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < a.C) dyv[c] = fmaf(wr[c], d, dyv[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < CMAX; ++c) {
-    if (c < a.C) {
-      const size_t o = ((size_t)n * a.C + c) * a.HW + p;
-      const float c0 = a.coef[((size_t)n * 2 + 0) * a.C + c], c1 = a.coef[((size_t)n * 2 + 1) * a.C + c];
-      a.dy[o] = fmaf(c0, a.dz[o], fmaf(-c1, yv[c], dyv[c]));
-    }
-  }
-}
-
 // Reduction over pixels: part[n][chunk][i][j] = sum_{p in chunk} A[n][i][p] * B[n][j][p], and rsum[n][chunk][i] = sum_p A[n][i][p]
-// (dW1 / db1 with A = da, B = y; dWr / dbr with A = dy, B = f).  64 x 64 output tiles, 32 pixels per shared-memory stage.
+// (dW1 / db1 with A = da, B = y; dWr / dbr with A = dy, B = f).  64 x 128 output tiles, 32 pixels per shared-memory stage; a
+// thread owns rows {4 ty ..} of A and rows {4 tx ..}, {64 + 4 tx ..} of B: three LDS.128 feed 32 FMAs per pixel.
 struct GramArgs {
   const float* A;   // [N][Ca][HW]
   const float* B;   // [N][Cb][HW]
@@ -464,38 +422,48 @@ struct GramArgs {
   int Ca, Cb, HW, chunk, chunks;
 };
 __global__ void __launch_bounds__(256) gram_px_kernel(const GramArgs a) {
-  __shared__ float sA[32][64 + 1];   // [px][row]
-  __shared__ float sB[32][64 + 1];
+  __shared__ __align__(16) float sA[32][64];    // [px][row]
+  __shared__ __align__(16) float sB[32][128];
   const int n = blockIdx.z / a.chunks, ch = blockIdx.z - n * a.chunks;
-  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;   // ty: rows of A, tx: rows of B
+  const int i0 = blockIdx.y * 64, j0 = blockIdx.x * 128;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int p_lo = ch * a.chunk, p_hi = min(a.HW, p_lo + a.chunk);
-  float acc[4][4];
+  float acc[4][8];
   float rs[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   const float* An = a.A + (size_t)n * a.Ca * a.HW;
   const float* Bn = a.B + (size_t)n * a.Cb * a.HW;
+  const int ra = threadIdx.x & 63, pa = (threadIdx.x >> 6) * 8;      // loader: row, first of 8 pixels  (A: 64 rows x 32 px)
+  const int rb = threadIdx.x & 127, pb = (threadIdx.x >> 7) * 16;    //                                 (B: 128 rows x 32 px)
   for (int p0 = p_lo; p0 < p_hi; p0 += 32) {
-    for (int t = threadIdx.x; t < 64 * 32; t += 256) {
-      const int r = t >> 5, px = t & 31;     // 32 consecutive pixels of one row: coalesced
-      const bool okp = p0 + px < p_hi;
-      sA[px][r] = (okp && i0 + r < a.Ca) ? __ldg(An + (size_t)(i0 + r) * a.HW + p0 + px) : 0.f;
-      sB[px][r] = (okp && j0 + r < a.Cb) ? __ldg(Bn + (size_t)(j0 + r) * a.HW + p0 + px) : 0.f;
+    {
+      const bool okr = i0 + ra < a.Ca;
+      const float* src = An + (size_t)(i0 + ra) * a.HW + p0 + pa;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sA[pa + e][ra] = (okr && p0 + pa + e < p_hi) ? __ldg(src + e) : 0.f;
+    }
+    {
+      const bool okr = j0 + rb < a.Cb;
+      const float* src = Bn + (size_t)(j0 + rb) * a.HW + p0 + pb;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) sB[pb + e][rb] = (okr && p0 + pb + e < p_hi) ? __ldg(src + e) : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
     for (int px = 0; px < 32; ++px) {
-      float av[4], bv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { av[i] = sA[px][ty * 4 + i]; bv[i] = sB[px][tx * 4 + i]; }
+      const float4 av = *reinterpret_cast<const float4*>(&sA[px][ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&sB[px][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&sB[px][64 + tx * 4]);
+      const float ar[4] = {av.x, av.y, av.z, av.w};
+      const float br[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        rs[i] += av[i];
+        rs[i] += ar[i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
       }
     }
     __syncthreads();
@@ -504,8 +472,10 @@ __global__ void __launch_bounds__(256) gram_px_kernel(const GramArgs a) {
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (i0 + ty * 4 + i < a.Ca && j0 + tx * 4 + j < a.Cb) o[(size_t)(i0 + ty * 4 + i) * a.Cb + j0 + tx * 4 + j] = acc[i][j];
+    for (int j = 0; j < 8; ++j) {
+      const int col = j0 + (j >> 2) * 64 + tx * 4 + (j & 3);
+      if (i0 + ty * 4 + i < a.Ca && col < a.Cb) o[(size_t)(i0 + ty * 4 + i) * a.Cb + col] = acc[i][j];
+    }
   if (a.rsum != nullptr && blockIdx.x == 0 && tx == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -613,39 +583,51 @@ extern "C" int halo_reduce_hfr_fwd(const float* feat, const float* Wr, const flo
 // ---- training mode ------------------------------------------------------------------------------------------------------
 namespace {
 struct TrainWs {
-  size_t part_sq, part_h, part_st, scale, bn, q, coef, v, part_bn, dbg, da, dy, gram, rsum, wrt, total;
-  int tiles, blocks, chunk, chunks;
+  size_t part_sq, part_h, part_st, scale, bn, q, coef, v, part_bn, dbg, da, dy, gram, rsum, wt, total;
+  int tiles, chunk, chunks;
 };
 TrainWs train_ws(int N, int Cin, int C, int H, int W) {
   TrainWs L;
   const size_t HW = (size_t)H * W;
   L.tiles = (int)((HW + RH_TP - 1) / RH_TP);
-  L.blocks = (int)((HW + 127) / 128);
-  size_t chunk = (HW + 15) / 16;
-  if (chunk < 2048) chunk = 2048;
+  size_t chunk = (HW + 63) / 64;     // pixel chunks of the gradient GEMMs: enough blocks to fill the GPU, at most 64 partials per image
+  if (chunk < 1024) chunk = 1024;
   chunk = (chunk + 31) / 32 * 32;
   L.chunk = (int)chunk;
   L.chunks = (int)((HW + chunk - 1) / chunk);
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off += rh_align(bytes); return o; };
   L.part_sq = take((size_t)N * L.tiles * C * 4);
-  L.part_h = take((size_t)N * L.blocks * C * 4);
-  L.part_st = take((size_t)N * L.blocks * 4 * 2 * C * 4);
+  L.part_h = take((size_t)N * C * 4);
+  L.part_st = take((size_t)N * C * 2 * 4);
   L.scale = take((size_t)N * C * 4);
   L.bn = take(2 * (size_t)C * 4);
   L.q = take((size_t)N * C * 4);
   L.coef = take((size_t)N * 2 * C * 4);
   L.v = take((size_t)N * C * 4);
-  L.part_bn = take((size_t)N * L.blocks * 2 * C * 4);
+  L.part_bn = take((size_t)N * 2 * C * 4);
   L.dbg = take(2 * (size_t)C * 4);
   L.da = take((size_t)N * C * HW * 4);
   L.dy = take((size_t)N * C * HW * 4);
   const size_t cmax = (size_t)(Cin > C ? Cin : C);
   L.gram = take((size_t)N * L.chunks * C * cmax * 4);
   L.rsum = take((size_t)N * L.chunks * C * 4);
-  L.wrt = take((size_t)Cin * C * 4);
+  L.wt = take(cmax * C * 4);
   L.total = off;
   return L;
+}
+int grid_for(long long total) {
+  long long b = (total + 255) / 256;
+  const long long cap = (long long)sm_count() * 16;
+  return (int)(b > cap ? cap : b);
+}
+int conv1x1(const float* in, const float* Wm, const float* bias, float* out, float* part_sq, int N, int Cin, int C, int HW, int tiles,
+            cudaStream_t st) {
+  ReduceArgs ra;
+  ra.f = in; ra.Wr = Wm; ra.br = bias; ra.y = out; ra.part_sq = part_sq;
+  ra.N = N; ra.Cin = Cin; ra.C = C; ra.HW = HW; ra.tiles = tiles;
+  reduce_kernel<<<dim3(tiles, (C + RH_TC - 1) / RH_TC, N), RH_THREADS, 0, st>>>(ra);
+  return launch_status("reduce_kernel");
 }
 }  // namespace
 
@@ -656,18 +638,14 @@ extern "C" size_t halo_reduce_hfr_train_workspace_bytes(int N, int Cin, int C, i
 
 extern "C" int halo_reduce_hfr_train_fwd(const float* feat, const float* Wr, const float* br, const float* W1, const float* b1,
                                          const float* bn_gamma, const float* bn_beta, float bn_eps, const float* W2,
-                                         const float* b2, const float* fixed_stats, float* y_out, float* z_out,
+                                         const float* b2, const float* fixed_stats, float* y_out, float* a_out, float* z_out,
                                          float* batch_stats, float* small, int N, int Cin, int C, int H, int W, void* ws,
                                          size_t ws_bytes, halo_stream_t stream) {
   HALO_CHECK_ARG(feat && Wr && y_out, "halo_reduce_hfr_train_fwd: NULL pointer");
   HALO_CHECK_ARG(N > 0 && Cin > 0 && C > 0 && H > 0 && W > 0 && N <= 65535, "halo_reduce_hfr_train_fwd: bad dims");
   const bool hfr = (W1 != nullptr);
-  HALO_CHECK_ARG(!hfr || (b1 && bn_gamma && bn_beta && W2 && b2 && z_out && batch_stats && small),
-                 "halo_reduce_hfr_train_fwd: the re-weighting MLP needs W1, b1, gamma, beta, W2, b2 and the z / statistics outputs");
-  if (hfr && C > 64) {
-    set_error("halo_reduce_hfr_train_fwd: training-mode HFR with %d reduced channels not compiled (<= 64)", C);
-    return HALO_ERR_UNSUPPORTED;
-  }
+  HALO_CHECK_ARG(!hfr || (b1 && bn_gamma && bn_beta && W2 && b2 && a_out && z_out && batch_stats && small),
+                 "halo_reduce_hfr_train_fwd: the re-weighting MLP needs W1, b1, gamma, beta, W2, b2 and the a / z / statistics outputs");
   const TrainWs L = train_ws(N, Cin, C, H, W);
   if (!ws || ws_bytes < L.total) {
     set_error("halo_reduce_hfr_train_fwd: workspace %zu < %zu bytes", ws_bytes, L.total);
@@ -682,62 +660,48 @@ extern "C" int halo_reduce_hfr_train_fwd(const float* feat, const float* Wr, con
   float* scale = (float*)(w8 + L.scale);
   float* bn = (float*)(w8 + L.bn);
 
-  ReduceArgs ra;
-  ra.f = feat; ra.Wr = Wr; ra.br = br; ra.y = y_out; ra.part_sq = hfr ? part_sq : nullptr;
-  ra.N = N; ra.Cin = Cin; ra.C = C; ra.HW = HW; ra.tiles = L.tiles;
-  reduce_kernel<<<dim3(L.tiles, (C + RH_TC - 1) / RH_TC, N), RH_THREADS, 0, st>>>(ra);
-  int rc = launch_status("reduce_kernel");
+  int rc = conv1x1(feat, Wr, br, y_out, hfr ? part_sq : nullptr, N, Cin, C, HW, L.tiles, st);
   if (rc || !hfr) return rc;
-
-  HiddenArgs ha;
-  ha.y = y_out; ha.W1 = W1; ha.b1 = b1; ha.bn_scale = bn; ha.bn_shift = bn + C; ha.part_h = part_h;
-  ha.N = N; ha.C = C; ha.HW = HW; ha.blocks = L.blocks;
-  const size_t smem = ((size_t)C * C + 4 * C) * 4;
+  rc = conv1x1(y_out, W1, b1, a_out, nullptr, N, C, C, HW, L.tiles, st);        // hidden pre-activations, kept for the backward
+  if (rc) return rc;
   if (fixed_stats != nullptr) {   // BatchNorm1d in evaluation mode inside a differentiated step: its running statistics
     HALO_CUDA(cudaMemcpyAsync(batch_stats, fixed_stats, 2 * (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
     bn_fold_kernel<<<1, 128, 0, st>>>(bn_gamma, bn_beta, fixed_stats, fixed_stats + C, bn_eps, bn, C);
     rc = launch_status("bn_fold_kernel");
-    if (rc) return rc;
   } else {
-    hidden_stats_kernel<64><<<dim3(L.blocks, N), 128, (size_t)C * C * 4, st>>>(ha, part_st);
-    rc = launch_status("hidden_stats_kernel");
+    plane_stats_kernel<<<N * C, 256, 0, st>>>(a_out, part_st, HW);
+    rc = launch_status("plane_stats_kernel");
     if (rc) return rc;
-    hidden_stats_finish_kernel<<<1, 64, 0, st>>>(part_st, N * L.blocks * 4, HW, L.blocks, C, bn_gamma, bn_beta, bn_eps, bn, batch_stats);
-    rc = launch_status("hidden_stats_finish_kernel");
-    if (rc) return rc;
+    plane_stats_finish_kernel<<<1, 128, 0, st>>>(part_st, N, HW, C, bn_gamma, bn_beta, bn_eps, bn, batch_stats);
+    rc = launch_status("plane_stats_finish_kernel");
   }
-  hidden_kernel<64><<<dim3(L.blocks, N), 128, smem, st>>>(ha);
-  rc = launch_status("hidden_kernel");
+  if (rc) return rc;
+  plane_hidden_sum_kernel<<<N * C, 256, 0, st>>>(a_out, bn, part_h, C, HW);
+  rc = launch_status("plane_hidden_sum_kernel");
   if (rc) return rc;
 
   ScaleArgs sa;
   sa.y = y_out; sa.part_sq = part_sq; sa.part_h = part_h; sa.W2 = W2; sa.b2 = b2; sa.scale = scale; sa.small = small;
-  sa.N = N; sa.C = C; sa.HW = HW; sa.tiles = L.tiles; sa.blocks = L.blocks;
+  sa.N = N; sa.C = C; sa.HW = HW; sa.tiles = L.tiles; sa.blocks = 1;
   hfr_scale_kernel<<<N, 128, (size_t)C * 4, st>>>(sa);
   rc = launch_status("hfr_scale_kernel");
   if (rc) return rc;
   const long long total = (long long)N * C * HW;
-  long long b = (total + 255) / 256;
-  if (b > (long long)sm_count() * 16) b = (long long)sm_count() * 16;
-  hfr_apply_oop_kernel<<<(int)b, 256, 0, st>>>(y_out, scale, z_out, HW, total);
+  hfr_apply_oop_kernel<<<grid_for(total), 256, 0, st>>>(y_out, scale, z_out, HW, total);
   return launch_status("hfr_apply_oop_kernel");
 }
 
-extern "C" int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, const float* W1, const float* b1,
-                                         const float* bn_gamma, const float* bn_beta, float bn_eps, const float* W2,
-                                         const float* y, const float* batch_stats, const float* small, const float* dz,
-                                         float* dfeat, float* dWr, float* dbr, float* dW1, float* db1, float* dgamma,
-                                         float* dbeta, float* dW2, float* db2, int stats_are_batch, int N, int Cin, int C, int H,
-                                         int W, void* ws, size_t ws_bytes, halo_stream_t stream) {
+extern "C" int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, const float* W1, const float* bn_gamma,
+                                         const float* bn_beta, float bn_eps, const float* W2, const float* y, const float* a,
+                                         const float* batch_stats, const float* small, const float* dz, float* dfeat,
+                                         float* dWr, float* dbr, float* dW1, float* db1, float* dgamma, float* dbeta, float* dW2,
+                                         float* db2, int stats_are_batch, int N, int Cin, int C, int H, int W, void* ws,
+                                         size_t ws_bytes, halo_stream_t stream) {
   HALO_CHECK_ARG(feat && Wr && dz && dWr, "halo_reduce_hfr_train_bwd: NULL pointer");
   HALO_CHECK_ARG(N > 0 && Cin > 0 && C > 0 && H > 0 && W > 0 && N <= 65535, "halo_reduce_hfr_train_bwd: bad dims");
   const bool hfr = (W1 != nullptr);
-  HALO_CHECK_ARG(!hfr || (b1 && bn_gamma && bn_beta && W2 && y && batch_stats && small && dW1 && db1 && dgamma && dbeta && dW2 && db2),
-                 "halo_reduce_hfr_train_bwd: the re-weighting MLP needs its parameters, the saved y / statistics and all gradient outputs");
-  if (hfr && C > 64) {
-    set_error("halo_reduce_hfr_train_bwd: training-mode HFR with %d reduced channels not compiled (<= 64)", C);
-    return HALO_ERR_UNSUPPORTED;
-  }
+  HALO_CHECK_ARG(!hfr || (bn_gamma && bn_beta && W2 && y && a && batch_stats && small && dW1 && db1 && dgamma && dbeta && dW2 && db2),
+                 "halo_reduce_hfr_train_bwd: the re-weighting MLP needs its parameters, the saved y / a / statistics and all gradient outputs");
   const TrainWs L = train_ws(N, Cin, C, H, W);
   if (!ws || ws_bytes < L.total) {
     set_error("halo_reduce_hfr_train_bwd: workspace %zu < %zu bytes", ws_bytes, L.total);
@@ -745,6 +709,7 @@ extern "C" int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, con
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int HW = H * W;
+  const long long total = (long long)N * C * HW;
   unsigned char* w8 = (unsigned char*)ws;
   float* bn = (float*)(w8 + L.bn);
   float* q = (float*)(w8 + L.q);
@@ -756,7 +721,7 @@ extern "C" int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, con
   float* dyb = (float*)(w8 + L.dy);
   float* gram = (float*)(w8 + L.gram);
   float* rsum = (float*)(w8 + L.rsum);
-  float* wrt = (float*)(w8 + L.wrt);
+  float* wt = (float*)(w8 + L.wt);
   int rc;
   const float* dy = dz;   // without the re-weighting the reduced features ARE the output
   if (hfr) {
@@ -774,30 +739,31 @@ extern "C" int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, con
     bn_fold_kernel<<<1, 128, 0, st>>>(bn_gamma, bn_beta, batch_stats, batch_stats + C, bn_eps, bn, C);
     rc = launch_status("bn_fold_kernel");
     if (rc) return rc;
-    HfrBnArgs ba;
-    ba.y = y; ba.W1 = W1; ba.b1 = b1; ba.bn = bn; ba.stats = batch_stats; ba.v = v; ba.eps = bn_eps; ba.part = part_bn;
-    ba.N = N; ba.C = C; ba.HW = HW; ba.blocks = L.blocks;
-    hfr_bwd_bn_sums_kernel<64><<<dim3(L.blocks, N), 128, ((size_t)C * C + 8 * C) * 4, st>>>(ba);
-    rc = launch_status("hfr_bwd_bn_sums_kernel");
+    plane_bn_sums_kernel<<<N * C, 256, 0, st>>>(a, bn, batch_stats, v, bn_eps, part_bn, C, HW);
+    rc = launch_status("plane_bn_sums_kernel");
     if (rc) return rc;
-    sum_partials_kernel<<<1, 128, 0, st>>>(part_bn, N * L.blocks, 2 * C, dbg);
+    sum_partials_kernel<<<1, 128, 0, st>>>(part_bn, N, 2 * C, dbg);
     rc = launch_status("sum_partials_kernel");
     if (rc) return rc;
     HALO_CUDA(cudaMemcpyAsync(dbeta, dbg, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
     HALO_CUDA(cudaMemcpyAsync(dgamma, dbg + C, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
-    HfrDaArgs da_a;
-    da_a.y = y; da_a.dz = dz; da_a.W1 = W1; da_a.b1 = b1; da_a.bn = bn; da_a.stats = batch_stats; da_a.v = v; da_a.dbg = dbg;
-    da_a.coef = coef; da_a.eps = bn_eps; da_a.da = da; da_a.dy = dyb; da_a.N = N; da_a.C = C; da_a.HW = HW;
     // statistics that do not depend on the batch (evaluation-mode BatchNorm): the two correction terms vanish
-    da_a.inv_m = stats_are_batch ? (float)(1.0 / ((double)N * HW)) : 0.f;
-    hfr_bwd_da_kernel<64><<<dim3(L.blocks, N), 128, (size_t)C * C * 4, st>>>(da_a);
-    rc = launch_status("hfr_bwd_da_kernel");
+    const float inv_m = stats_are_batch ? (float)(1.0 / ((double)N * HW)) : 0.f;
+    hfr_da_elem_kernel<<<grid_for(total), 256, 0, st>>>(a, bn, batch_stats, v, dbg, bn_eps, inv_m, da, C, HW, total);
+    rc = launch_status("hfr_da_elem_kernel");
+    if (rc) return rc;
+    // dy = W1^T da + (normalise * weight part)
+    transpose_kernel<<<(C * C + 255) / 256, 256, 0, st>>>(W1, wt, C, C);
+    rc = conv1x1(da, wt, nullptr, dyb, nullptr, N, C, C, HW, L.tiles, st);
+    if (rc) return rc;
+    hfr_dy_finish_kernel<<<grid_for(total), 256, 0, st>>>(dyb, dz, y, coef, C, HW, total);
+    rc = launch_status("hfr_dy_finish_kernel");
     if (rc) return rc;
     dy = dyb;
     // dW1 = sum da (x) y, db1 = sum da
     GramArgs g1;
     g1.A = da; g1.B = y; g1.part = gram; g1.rsum = rsum; g1.Ca = C; g1.Cb = C; g1.HW = HW; g1.chunk = L.chunk; g1.chunks = L.chunks;
-    gram_px_kernel<<<dim3((C + 63) / 64, (C + 63) / 64, N * L.chunks), 256, 0, st>>>(g1);
+    gram_px_kernel<<<dim3((C + 127) / 128, (C + 63) / 64, N * L.chunks), 256, 0, st>>>(g1);
     rc = launch_status("gram_px_kernel");
     if (rc) return rc;
     sum_partials_kernel<<<(C * C + 127) / 128, 128, 0, st>>>(gram, N * L.chunks, C * C, dW1);
@@ -808,20 +774,16 @@ extern "C" int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, con
   // dWr = sum dy (x) f, dbr = sum dy
   GramArgs g2;
   g2.A = dy; g2.B = feat; g2.part = gram; g2.rsum = rsum; g2.Ca = C; g2.Cb = Cin; g2.HW = HW; g2.chunk = L.chunk; g2.chunks = L.chunks;
-  gram_px_kernel<<<dim3((Cin + 63) / 64, (C + 63) / 64, N * L.chunks), 256, 0, st>>>(g2);
+  gram_px_kernel<<<dim3((Cin + 127) / 128, (C + 63) / 64, N * L.chunks), 256, 0, st>>>(g2);
   rc = launch_status("gram_px_kernel");
   if (rc) return rc;
   sum_partials_kernel<<<(C * Cin + 127) / 128, 128, 0, st>>>(gram, N * L.chunks, C * Cin, dWr);
   if (dbr != nullptr) sum_partials_kernel<<<1, 128, 0, st>>>(rsum, N * L.chunks, C, dbr);
   rc = launch_status("sum_partials_kernel");
   if (rc) return rc;
-  if (dfeat != nullptr) {   // df = Wr^T dy: the same register-tile kernel as the forward, with the transposed weight
-    transpose_kernel<<<(C * Cin + 255) / 256, 256, 0, st>>>(Wr, wrt, C, Cin);
-    ReduceArgs ra;
-    ra.f = dy; ra.Wr = wrt; ra.br = nullptr; ra.y = dfeat; ra.part_sq = nullptr;
-    ra.N = N; ra.Cin = C; ra.C = Cin; ra.HW = HW; ra.tiles = L.tiles;
-    reduce_kernel<<<dim3(L.tiles, (Cin + RH_TC - 1) / RH_TC, N), RH_THREADS, 0, st>>>(ra);
-    rc = launch_status("reduce_kernel (dfeat)");
+  if (dfeat != nullptr) {   // df = Wr^T dy: the forward's own tile kernel with the transposed weight
+    transpose_kernel<<<(C * Cin + 255) / 256, 256, 0, st>>>(Wr, wt, C, Cin);
+    rc = conv1x1(dy, wt, nullptr, dfeat, nullptr, N, C, Cin, HW, L.tiles, st);
   }
   return rc;
 }

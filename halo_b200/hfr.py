@@ -71,16 +71,17 @@ class _ReduceHFRTrain(torch.autograd.Function):
         hfr = W1 is not None
         y = torch.empty((N, C, H, W), dtype=torch.float32, device=dev)
         z = torch.empty_like(y) if hfr else None
+        a = torch.empty_like(y) if hfr else None
         stats = torch.empty((2, C), dtype=torch.float32, device=dev) if hfr else None
         small = torch.empty((N, 3, C), dtype=torch.float32, device=dev) if hfr else None
         ws = nat.workspace.get(dev, "reduce_hfr_train", lib.halo_reduce_hfr_train_workspace_bytes(N, Cin, C, H, W))
         with torch.cuda.device(dev):
             rc = lib.halo_reduce_hfr_train_fwd(nat.ptr(x), nat.ptr(Wr), nat.ptr(br), nat.ptr(W1), nat.ptr(b1), nat.ptr(g), nat.ptr(b),
-                                               eps, nat.ptr(W2), nat.ptr(b2), nat.ptr(fixed_stats), nat.ptr(y), nat.ptr(z),
+                                               eps, nat.ptr(W2), nat.ptr(b2), nat.ptr(fixed_stats), nat.ptr(y), nat.ptr(a), nat.ptr(z),
                                                nat.ptr(stats), nat.ptr(small), N, Cin, C, H, W, nat.ptr(ws), ws.numel(),
                                                nat.stream_of(x))
         nat.check(rc, "halo_reduce_hfr_train_fwd")
-        ctx.save_for_backward(x, Wr, W1, b1, g, b, W2, y, stats, small)
+        ctx.save_for_backward(x, Wr, W1, g, b, W2, y, a, stats, small)
         ctx.meta = (eps, dims, fixed_stats is None, br is not None)
         ctx.mark_non_differentiable(*([stats] if hfr else []))
         return (z, stats) if hfr else (y, None)
@@ -88,7 +89,7 @@ class _ReduceHFRTrain(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz, _dstats):
         lib = nat.load()
-        x, Wr, W1, b1, g, b, W2, y, stats, small = ctx.saved_tensors
+        x, Wr, W1, g, b, W2, y, a, stats, small = ctx.saved_tensors
         eps, (N, Cin, C, H, W), batch, has_br = ctx.meta
         dev = x.device
         hfr = W1 is not None
@@ -102,8 +103,8 @@ class _ReduceHFRTrain(torch.autograd.Function):
             db1, dg, db, db2 = (torch.empty((C,), **f32) for _ in range(4))
         ws = nat.workspace.get(dev, "reduce_hfr_train", lib.halo_reduce_hfr_train_workspace_bytes(N, Cin, C, H, W))
         with torch.cuda.device(dev):
-            rc = lib.halo_reduce_hfr_train_bwd(nat.ptr(x), nat.ptr(Wr), nat.ptr(W1), nat.ptr(b1), nat.ptr(g), nat.ptr(b), eps,
-                                               nat.ptr(W2), nat.ptr(y), nat.ptr(stats), nat.ptr(small), nat.ptr(dz), nat.ptr(dx),
+            rc = lib.halo_reduce_hfr_train_bwd(nat.ptr(x), nat.ptr(Wr), nat.ptr(W1), nat.ptr(g), nat.ptr(b), eps,
+                                               nat.ptr(W2), nat.ptr(y), nat.ptr(a), nat.ptr(stats), nat.ptr(small), nat.ptr(dz), nat.ptr(dx),
                                                nat.ptr(dWr), nat.ptr(dbr), nat.ptr(dW1), nat.ptr(db1), nat.ptr(dg), nat.ptr(db),
                                                nat.ptr(dW2), nat.ptr(db2), 1 if batch else 0, N, Cin, C, H, W, nat.ptr(ws),
                                                ws.numel(), nat.stream_of(x))

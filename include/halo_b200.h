@@ -229,7 +229,8 @@ int halo_reduce_hfr_fwd(const float* feat, const float* Wr, const float* br, con
 
 /* Training mode of the same block (the training step's side of classifier.py:526-550): BatchNorm1d normalises with the
  * statistics of the batch (all N*H*W rows), and halo_reduce_hfr_train_bwd is the autograd of the whole block.
- *   fwd: y_out [N,C,H,W] = conv_reduce(f) (kept for the backward); z_out [N,C,H,W] = the re-weighted features (W1 = NULL:
+ *   fwd: y_out [N,C,H,W] = conv_reduce(f) and a_out [N,C,H,W] = the hidden pre-activations W1 y + b1 (both kept for the
+ *        backward); z_out [N,C,H,W] = the re-weighted features (W1 = NULL:
  *        no HFR, z = y, z_out unused); batch_stats [2][C] = batch mean and biased variance of the hidden pre-activations
  *        (the caller updates running_mean / running_var from them, the variance times M/(M-1), M = N*H*W);
  *        small [N][3][C] = per-image {mean hidden activation, re-weighting before the clamp, |y_c|} for the backward.
@@ -237,15 +238,16 @@ int halo_reduce_hfr_fwd(const float* feat, const float* Wr, const float* br, con
  *        dW2 [C,C], db2 (all overwritten).  Fixed-order reductions: bitwise reproducible.
  *   fixed_stats [2][C] | NULL: a BatchNorm1d left in evaluation mode inside a differentiated step normalises with its
  *        running mean / variance; pass them here (they are copied to batch_stats) and stats_are_batch = 0 to the backward.
- * Training-mode HFR needs C <= 64 (the channel count of every shipped HALO config); one workspace size serves both calls. */
+ * One workspace size serves both calls. */
 size_t halo_reduce_hfr_train_workspace_bytes(int N, int Cin, int C, int H, int W);
 int halo_reduce_hfr_train_fwd(const float* feat, const float* Wr, const float* br, const float* W1, const float* b1,
                               const float* bn_gamma, const float* bn_beta, float bn_eps, const float* W2, const float* b2,
-                              const float* fixed_stats, float* y_out, float* z_out, float* batch_stats, float* small, int N,
-                              int Cin, int C, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
-int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, const float* W1, const float* b1, const float* bn_gamma,
-                              const float* bn_beta, float bn_eps, const float* W2, const float* y, const float* batch_stats,
-                              const float* small, const float* dz, float* dfeat, float* dWr, float* dbr, float* dW1,
+                              const float* fixed_stats, float* y_out, float* a_out, float* z_out, float* batch_stats,
+                              float* small, int N, int Cin, int C, int H, int W, void* ws, size_t ws_bytes,
+                              halo_stream_t stream);
+int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, const float* W1, const float* bn_gamma,
+                              const float* bn_beta, float bn_eps, const float* W2, const float* y, const float* a,
+                              const float* batch_stats, const float* small, const float* dz, float* dfeat, float* dWr, float* dbr, float* dW1,
                               float* db1, float* dgamma, float* dbeta, float* dW2, float* db2, int stats_are_batch, int N,
                               int Cin, int C, int H, int W, void* ws, size_t ws_bytes, halo_stream_t stream);
 
