@@ -63,10 +63,12 @@ def test_acquire_full_size_matches_oracle(name, cfg, shape, expect):
         assert len(got & want) >= 0.999 * expect, (name, i, len(got & want))
 
 
-def test_head_tensor_core_eight_full_size_images_one_launch():
+@pytest.mark.parametrize("C", [256, 64], ids=["c256-one-epilogue-warpgroup", "c64-two-epilogue-warpgroups"])
+def test_head_tensor_core_eight_full_size_images_one_launch(C):
     """K1-TC vs K1-CUDA-core vs the fp64 oracle: logits, radius, pixel entropy, label and per-image min/max over
-    8 x 1280x640 px in a single launch (51 200 tiles over 148 persistent CTAs)."""
-    N, C, O, H, W = 8, 256, 19, 640, 1280
+    8 x 1280x640 px in a single launch (51 200 tiles over 148 persistent CTAs) -- at the BASELINE channel count and at 64,
+    the channel count of every shipped HALO config (core/configs/defaults.py:14), where the kernel runs its 640-thread form."""
+    N, O, H, W = 8, 19, 640, 1280
     P, A = synth.head_params(O, C, seed=0, dtype=torch.float64)
     u = torch.empty((N, C, H, W), dtype=torch.float32, device=DEV)
     for i in range(N):
