@@ -545,13 +545,22 @@ def run_side_configs(feat, gt, st, dev):
              ("BASELINE.json configs[3] SYNTHIA-shaped: 16 classes, 5x5 regions, 2.2 %% budget = 721 picks/img", 16,
               halo_b200.AcquisitionConfig(num_classes=16, curvature=w["curvature"], radius_k=2, mask_radius_k=w["mask_radius_k"],
                                           budget=0.022, n_rounds=1, uncertainty="entropy", purity="radius", normalize=True))]
+    if B % 4 == 0 and C % 4 == 0:
+        # (c) the head width every shipped HALO config uses (REDUCED_CHANNELS 64, core/configs/defaults.py:14): the first
+        #     quarter of the resident bytes viewed as B images of C/4 channels -- same pixels per step as the headline
+        cases.append(("headline configuration at the shipped head width: %d-d features (a quarter of the bytes per pixel)" % (C // 4),
+                      w["O"], cases[0][2].__class__(num_classes=w["O"], curvature=w["curvature"], radius_k=1,
+                                                   mask_radius_k=w["mask_radius_k"], budget=w["budget"], n_rounds=1,
+                                                   uncertainty="entropy", purity="radius", normalize=True)))
     for name, O, cfg in cases:
-        P, A = synth.head_params(O, C, seed=0, device=dev)
+        narrow = "shipped head width" in name
+        fx = feat[:B // 4].reshape(B, C // 4, H, W) if narrow else feat
+        P, A = synth.head_params(O, fx.shape[1], seed=0, device=dev)
         g = gt if O == w["O"] else torch.where(gt == 255, gt, gt % O)
 
         def step():
             st["active"].zero_(); st["selected"].zero_(); st["active_mask"].fill_(255)
-            return halo_b200.acquire_batch(feat, P, A, cfg, g, st["active"], st["selected"], st["active_mask"])
+            return halo_b200.acquire_batch(fx, P, A, cfg, g, st["active"], st["selected"], st["active_mask"])
 
         for _ in range(2):
             res = step()
@@ -563,7 +572,7 @@ def run_side_configs(feat, gt, st, dev):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        out.append({"workload": name % (), "ms_per_step": round(ms, 3), "Mpixel/s": round(B * H * W / ms / 1e3, 1),
+        out.append({"workload": name if narrow else name % (), "ms_per_step": round(ms, 3), "Mpixel/s": round(B * H * W / ms / 1e3, 1),
                     "picks_per_image": int(res["n_picked"].min().item()), "images_per_step": B,
                     "note": "includes the three state-plane resets per step"})
     return out
