@@ -207,6 +207,48 @@ def train_fixtures():
     out["hfr_c"] = np.float64(clf.conv_seg.c)
     out["hfr_logits"] = logits.numpy()
     out["hfr_emb"] = emb.numpy()
+    # the same classifier class in TRAINING mode (BatchNorm on batch statistics), one forward + backward on the CPU: what the
+    # block conv_reduce + HFR + head (:526-554) receives (input of conv_reduce), returns (logits) and back-propagates
+    # (gradient w.r.t. that input, gradients of every parameter of conv_reduce / wn_mlp / conv_seg, BatchNorm1d bookkeeping)
+    torch.manual_seed(13)
+    with ref_import.cpu_only():
+        clf_t = side.classifier.DepthwiseSeparableASPP_Hyper(inplanes=48, dilation_series=[1, 2], padding_series=[1, 2],
+                                                             num_classes=O, norm_layer=nn.BatchNorm2d, reduced_channels=C, hfr=True)
+    with torch.no_grad():
+        for mod in clf_t.modules():
+            if isinstance(mod, (nn.BatchNorm1d, nn.BatchNorm2d)):
+                mod.running_mean.uniform_(-0.2, 0.2)
+                mod.running_var.uniform_(0.5, 1.5)
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.uniform_(-0.2, 0.2)
+    clf_t.train()
+    lin1, bn, lin2 = clf_t.wn_mlp[0], clf_t.wn_mlp[1], clf_t.wn_mlp[3]
+    named = (("Wr", clf_t.conv_reduce.weight), ("br", clf_t.conv_reduce.bias), ("W1", lin1.weight), ("b1", lin1.bias),
+             ("bn_w", bn.weight), ("bn_b", bn.bias), ("W2", lin2.weight), ("b2", lin2.bias), ("P", clf_t.conv_seg.P_MLR),
+             ("A", clf_t.conv_seg.A_MLR))
+    for name, t_ in named:
+        out["hfrt_" + name] = t_.detach().numpy().copy()
+    out["hfrt_bn_mean0"] = bn.running_mean.numpy().copy()
+    out["hfrt_bn_var0"] = bn.running_var.numpy().copy()
+    out["hfrt_bn_momentum"] = np.float64(bn.momentum)
+    cap = {}
+    clf_t.conv_reduce.register_forward_hook(lambda m, i, o: cap.update(f=i[0].detach().clone()))
+    clf_t.conv_reduce.register_full_backward_hook(lambda m, gi, go: cap.update(df=gi[0].detach().clone()))
+    xt = {"out": torch.randn(3, 48, 9, 12), "low": torch.randn(3, 256, 18, 24)}
+    with ref_import.cpu_only():
+        logits_t, _ = clf_t(xt, size=None)
+    R = torch.randn(logits_t.shape, generator=torch.Generator().manual_seed(14))
+    (logits_t * R).sum().backward()
+    out["hfrt_f"] = cap["f"].numpy()
+    out["hfrt_df"] = cap["df"].numpy()
+    out["hfrt_R"] = R.numpy()
+    out["hfrt_logits"] = logits_t.detach().numpy()
+    for name, t_ in named:
+        out["hfrt_d" + name] = t_.grad.detach().numpy()
+    out["hfrt_bn_mean1"] = bn.running_mean.numpy().copy()
+    out["hfrt_bn_var1"] = bn.running_var.numpy().copy()
+    out["hfrt_bn_eps"] = np.float64(bn.eps)
+    out["hfrt_c"] = np.float64(clf_t.conv_seg.c)
     # loss sequence
     neg_crit = side.NegativeLearningLoss(threshold=0.05)
     g = torch.Generator().manual_seed(12)

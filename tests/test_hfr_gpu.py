@@ -146,7 +146,7 @@ def test_reduce_hfr_training_mode_chains_into_the_fused_head_and_loss():
     out = head(mapper.expmap(zz, dim=1))
     loss = fused_seg_loss(out, labels.to(DEV), (4 * H, 4 * W), 1.0, 0.05)[0]
     loss.backward()
-    assert abs(float(loss) - float(loss_ref)) <= 1e-5 * max(1.0, abs(float(loss_ref)))
+    assert abs(float(loss.detach()) - float(loss_ref.detach())) <= 1e-5 * max(1.0, abs(float(loss_ref)))
     assert rel_err(convd.weight.grad, conv.weight.grad) <= 2e-4
     assert rel_err(mlpd[0].weight.grad, mlp[0].weight.grad) <= 2e-4
     assert rel_err(head.P_MLR.grad, Pr.grad) <= 2e-4
@@ -170,3 +170,24 @@ def test_reference_classifier_golden(golden):
         out = mlr(emb.double()).float()                  # classifier.py:554
     assert rel_err(out, t(g["hfr_logits"])) <= 2 * TOL
     assert rel_err(emb.materialize(), t(g["hfr_emb"])) <= 2 * TOL
+
+
+def test_reference_classifier_training_step_golden(golden):
+    """One training step of conv_reduce + HFR + fused head on the GPU against the forward + backward of the reference's real
+    classifier class in training mode (tests/golden/train.npz, frozen from the live reference): logits, the gradient w.r.t.
+    the decoder features, every parameter gradient, BatchNorm1d running statistics."""
+    from tests.test_oracle_golden import _hfr_train_modules, check_hfr_train_grads, t
+
+    g = golden["train"]
+    conv, mlp = _hfr_train_modules(g)
+    conv, mlp = conv.to(DEV), mlp.to(DEV)
+    c = float(g["hfrt_c"])
+    mapper = halo_b200.HyperMapper(c=c)
+    mlr = halo_b200.HyperMLR(conv.weight.shape[0], 19, c=c).to(DEV)
+    mlr.load_state_dict({"P_MLR": t(g["hfrt_P"]), "A_MLR": t(g["hfrt_A"])})
+    f = t(g["hfrt_f"]).to(DEV).requires_grad_(True)
+    z = reduce_hfr(f, conv, mlp)                         # classifier.py:527-550, training mode
+    out = mlr(mapper.expmap(z, dim=1).double()).float()  # :553-554
+    assert rel_err(out, t(g["hfrt_logits"])) <= 2 * TOL
+    (out * t(g["hfrt_R"]).to(DEV)).sum().backward()
+    check_hfr_train_grads(g, conv, mlp, f.grad, mlr.P_MLR.grad, mlr.A_MLR.grad, 2e-4)

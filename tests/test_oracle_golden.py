@@ -144,6 +144,66 @@ def test_hfr_and_head_call_site_match_the_reference_classifier(golden):
     assert (logits - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
 
 
+def _hfr_train_modules(g, dtype=torch.float32):
+    """conv_reduce / wn_mlp of the reference's TRAINING-mode classifier instance, as they were before its step."""
+    import torch.nn as nn
+
+    Wr = t(g["hfrt_Wr"])
+    C, Cin = Wr.shape[0], Wr.shape[1]
+    conv = nn.Conv2d(Cin, C, kernel_size=1)
+    mlp = nn.Sequential(nn.Linear(C, C), nn.BatchNorm1d(C, eps=float(g["hfrt_bn_eps"]), momentum=float(g["hfrt_bn_momentum"])),
+                        nn.ReLU(), nn.Linear(C, C))
+    with torch.no_grad():
+        conv.weight.copy_(Wr); conv.bias.copy_(t(g["hfrt_br"]))
+        mlp[0].weight.copy_(t(g["hfrt_W1"])); mlp[0].bias.copy_(t(g["hfrt_b1"]))
+        mlp[1].weight.copy_(t(g["hfrt_bn_w"])); mlp[1].bias.copy_(t(g["hfrt_bn_b"]))
+        mlp[1].running_mean.copy_(t(g["hfrt_bn_mean0"])); mlp[1].running_var.copy_(t(g["hfrt_bn_var0"]))
+        mlp[3].weight.copy_(t(g["hfrt_W2"])); mlp[3].bias.copy_(t(g["hfrt_b2"]))
+    return conv.to(dtype).train(), mlp.to(dtype).train()
+
+
+HFRT_PARAMS = (("dWr", lambda c, m: c.weight), ("dbr", lambda c, m: c.bias), ("dW1", lambda c, m: m[0].weight),
+               ("db1", lambda c, m: m[0].bias), ("dbn_w", lambda c, m: m[1].weight), ("dbn_b", lambda c, m: m[1].bias),
+               ("dW2", lambda c, m: m[3].weight), ("db2", lambda c, m: m[3].bias))
+
+
+def check_hfr_train_grads(g, conv, mlp, df, dP, dA, tol):
+    """Gradients of one training step of the block against the golden vectors of the reference's own classifier class; every
+    parameter gradient is measured against the larger of its own magnitude and 1e-2 of the largest one (the bias in front of
+    a batch-statistics BatchNorm has an exactly zero gradient)."""
+    refs = {k: t(g["hfrt_" + k]) for k, _ in HFRT_PARAMS}
+    floor = 1e-2 * max(float(v.abs().max()) for v in refs.values())
+    for k, get in HFRT_PARAMS:
+        got = get(conv, mlp).grad.detach().cpu().double().reshape(refs[k].shape)
+        err = float((got - refs[k].double()).abs().max()) / max(float(refs[k].abs().max()), floor)
+        assert err <= tol, (k, err)
+    for got, key in ((df, "hfrt_df"), (dP, "hfrt_dP"), (dA, "hfrt_dA")):
+        ref = t(g[key]).double()
+        assert float((got.detach().cpu().double() - ref).abs().max()) <= tol * float(ref.abs().max()), key
+    bn = mlp[1]
+    for got, key in ((bn.running_mean, "hfrt_bn_mean1"), (bn.running_var, "hfrt_bn_var1")):
+        ref = t(g[key]).double()
+        assert float((got.detach().cpu().double() - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), key
+
+
+def test_hfr_training_step_matches_the_reference_classifier(golden):
+    """oracle/hfr.py + oracle/head.py in TRAINING mode against one forward + backward of the reference's real classifier
+    class (DepthwiseSeparableASPP_Hyper, classifier.py:526-554; BatchNorm1d on batch statistics): logits, the gradient that
+    reaches the decoder features, every parameter gradient of conv_reduce / wn_mlp / conv_seg, and the running statistics."""
+    from oracle import hfr as ohfr
+
+    g = golden["train"]
+    conv, mlp = _hfr_train_modules(g)
+    f = t(g["hfrt_f"]).clone().requires_grad_(True)
+    P, A = t(g["hfrt_P"]).clone().requires_grad_(True), t(g["hfrt_A"]).clone().requires_grad_(True)
+    z = ohfr.reduce_hfr(f, conv, mlp)
+    logits = ohead.mlr_logits(ohead.expmap(z, float(g["hfrt_c"]), dim=1).double(), P, A, float(g["hfrt_c"])).float()
+    ref = t(g["hfrt_logits"])
+    assert (logits - ref).abs().max().item() <= 1e-6 * ref.abs().max().item()
+    (logits * t(g["hfrt_R"])).sum().backward()
+    check_hfr_train_grads(g, conv, mlp, f.grad, P.grad, A.grad, 1e-5)
+
+
 def test_loss_oracle_matches_the_reference_sequence(golden):
     """oracle/loss.py against the learner's sequence run with the reference's own NegativeLearningLoss class."""
     from oracle import loss as oloss
