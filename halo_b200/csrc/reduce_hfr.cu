@@ -230,39 +230,43 @@ __global__ void hfr_apply_scalar_kernel(float* __restrict__ y, const float* __re
 // The hidden pre-activations a = W1 y + b1 are one more 1x1 convolution (reduce_kernel with Cin = C) kept as a plane tensor
 // [N][C][HW]; everything BatchNorm / ReLU needs in either direction is then a per-plane reduction or an element-wise pass.
 
-// fixed-order block sum of one value per thread (256 threads)
-__device__ __forceinline__ float block_sum_256(float v, float* red) {
+// fixed-order block sum of one value per thread (256 threads).  The plane sums are accumulated in DOUBLE: the backward's
+// BatchNorm terms cancel over all N*HW pixels (sum of da = 0), so a 1e-5 relative error in a plane sum -- what 200
+// same-signed fp32 additions per thread give -- comes back multiplied by the pixel count in dW1 and dfeat.
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
   red[threadIdx.x] = v;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  const float r = red[0];
+  const double r = red[0];
   __syncthreads();
   return r;
 }
 
 // one block per (n, j) plane: sum and M2 about the plane's own mean (two passes over an L2-resident plane; a one-pass
-// E[a^2] - mean^2 in fp32 loses the variance when |mean| >> sigma)
-__global__ void __launch_bounds__(256) plane_stats_kernel(const float* __restrict__ a, float* __restrict__ part /* [planes][2] */, int HW) {
-  __shared__ float red[256];
+// E[a^2] - mean^2 loses the variance when |mean| >> sigma)
+__global__ void __launch_bounds__(256) plane_stats_kernel(const float* __restrict__ a, double* __restrict__ part /* [planes][2] */, int HW) {
+  __shared__ double red[256];
   const float* pl = a + (size_t)blockIdx.x * HW;
-  float s = 0.f;
-  for (int p = threadIdx.x; p < HW; p += 256) s += pl[p];
-  const float sum = block_sum_256(s, red);
-  const float mean = sum / (float)HW;
-  float m2 = 0.f;
+  double s = 0.0;
+  for (int p = threadIdx.x; p < HW; p += 256) s += (double)pl[p];
+  const double sum = block_sum_256(s, red);
+  const float mean = (float)(sum / (double)HW);
+  double m2 = 0.0;
   for (int p = threadIdx.x; p < HW; p += 256) {
     const float d = pl[p] - mean;
-    m2 = fmaf(d, d, m2);
+    m2 += (double)(d * d);
   }
   m2 = block_sum_256(m2, red);
-  if (threadIdx.x == 0) { part[2 * blockIdx.x] = sum; part[2 * blockIdx.x + 1] = m2; }
+  // M2 about the rounded mean -> about the exact one: sum (a - m)^2 = sum (a - mf)^2 - HW (m - mf)^2
+  const double dm = sum / (double)HW - (double)mean;
+  if (threadIdx.x == 0) { part[2 * blockIdx.x] = sum; part[2 * blockIdx.x + 1] = m2 - (double)HW * dm * dm; }
 }
 
 // combine the N planes of every hidden unit in a fixed order (double), fold the batch statistics into scale / shift
-__global__ void plane_stats_finish_kernel(const float* __restrict__ part, int N, int HW, int C, const float* g, const float* b, float eps,
+__global__ void plane_stats_finish_kernel(const double* __restrict__ part, int N, int HW, int C, const float* g, const float* b, float eps,
                                           float* bn /* [2][C] */, float* stats /* [2][C] */) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < C; j += gridDim.x * blockDim.x) {
     double S = 0.0;
@@ -285,31 +289,32 @@ __global__ void plane_stats_finish_kernel(const float* __restrict__ part, int N,
 // one block per (n, j) plane: sum over the pixels of relu(bn(a)) -> part_h[n][j]
 __global__ void __launch_bounds__(256) plane_hidden_sum_kernel(const float* __restrict__ a, const float* __restrict__ bn, float* __restrict__ out,
                                                                int C, int HW) {
-  __shared__ float red[256];
+  __shared__ double red[256];
   const int j = blockIdx.x % C;
   const float sc = bn[j], sh = bn[C + j];
   const float* pl = a + (size_t)blockIdx.x * HW;
-  float s = 0.f;
-  for (int p = threadIdx.x; p < HW; p += 256) s += fmaxf(fmaf(pl[p], sc, sh), 0.f);
+  double s = 0.0;
+  for (int p = threadIdx.x; p < HW; p += 256) s += (double)fmaxf(fmaf(pl[p], sc, sh), 0.f);
   s = block_sum_256(s, red);
-  if (threadIdx.x == 0) out[blockIdx.x] = s;
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)s;
 }
 
 // one block per (n, j) plane: sum g and sum g * x_hat with g = v[n][j] * [bn(a) > 0]  -> part[n][2][C]
 __global__ void __launch_bounds__(256) plane_bn_sums_kernel(const float* __restrict__ a, const float* __restrict__ bn, const float* __restrict__ stats,
-                                                            const float* __restrict__ v, float eps, float* __restrict__ part, int C, int HW) {
-  __shared__ float red[256];
+                                                            const float* __restrict__ v, float eps, double* __restrict__ part, int C, int HW) {
+  __shared__ double red[256];
   const int n = blockIdx.x / C, j = blockIdx.x - n * C;
-  const float sc = bn[j], sh = bn[C + j], mean = stats[j], isd = rsqrtf(stats[C + j] + eps), vj = v[blockIdx.x];
+  const float sc = bn[j], sh = bn[C + j], mean = stats[j], isd = rsqrtf(stats[C + j] + eps);
+  const double vj = (double)v[blockIdx.x];
   const float* pl = a + (size_t)blockIdx.x * HW;
-  float g = 0.f, gx = 0.f;
+  double cnt = 0.0, sx = 0.0;     // number of active pixels, sum of their x_hat
   for (int p = threadIdx.x; p < HW; p += 256) {
     const float t = pl[p];
-    if (fmaf(t, sc, sh) > 0.f) { g += vj; gx = fmaf(vj, (t - mean) * isd, gx); }
+    if (fmaf(t, sc, sh) > 0.f) { cnt += 1.0; sx += (double)((t - mean) * isd); }
   }
-  g = block_sum_256(g, red);
-  gx = block_sum_256(gx, red);
-  if (threadIdx.x == 0) { part[((size_t)n * 2 + 0) * C + j] = g; part[((size_t)n * 2 + 1) * C + j] = gx; }
+  cnt = block_sum_256(cnt, red);
+  sx = block_sum_256(sx, red);
+  if (threadIdx.x == 0) { part[((size_t)n * 2 + 0) * C + j] = vj * cnt; part[((size_t)n * 2 + 1) * C + j] = vj * sx; }
 }
 
 // element-wise: da = gamma/sigma (g - dbeta/M - x_hat dgamma/M)
@@ -341,19 +346,19 @@ __global__ void hfr_apply_oop_kernel(const float* __restrict__ y, const float* _
     z[g] = y[g] * scale[g / HW];
 }
 
-// q[plane] = sum_p a[plane][p] * b[plane][p], one block per (n, c) plane, fixed-order tree
+// q[plane] = sum_p a[plane][p] * b[plane][p], one block per (n, c) plane, fixed-order tree, double accumulation
 __global__ void __launch_bounds__(256) dot_planes_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ q, int HW) {
-  __shared__ float red[256];
+  __shared__ double red[256];
   const size_t base = (size_t)blockIdx.x * HW;
-  float s = 0.f;
-  for (int p = threadIdx.x; p < HW; p += 256) s = fmaf(a[base + p], b[base + p], s);
+  double s = 0.0;
+  for (int p = threadIdx.x; p < HW; p += 256) s += (double)a[base + p] * (double)b[base + p];
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) q[blockIdx.x] = red[0];
+  if (threadIdx.x == 0) q[blockIdx.x] = (float)red[0];
 }
 
 struct HfrSmallArgs {
@@ -402,6 +407,13 @@ __global__ void hfr_bwd_small_kernel(const HfrSmallArgs a) {
   }
 }
 
+__global__ void sum_partials_f64_kernel(const double* __restrict__ part, int groups, int rows, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int g = 0; g < groups; ++g) s += part[(size_t)g * rows + i];
+    out[i] = (float)s;
+  }
+}
 // fixed-order finish of [groups][rows] partials in double: out[i] = sum_g part[g][i]
 __global__ void sum_partials_kernel(const float* __restrict__ part, int groups, int rows, float* __restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += gridDim.x * blockDim.x) {
@@ -599,13 +611,13 @@ TrainWs train_ws(int N, int Cin, int C, int H, int W) {
   auto take = [&](size_t bytes) { size_t o = off; off += rh_align(bytes); return o; };
   L.part_sq = take((size_t)N * L.tiles * C * 4);
   L.part_h = take((size_t)N * C * 4);
-  L.part_st = take((size_t)N * C * 2 * 4);
+  L.part_st = take((size_t)N * C * 2 * 8);
   L.scale = take((size_t)N * C * 4);
   L.bn = take(2 * (size_t)C * 4);
   L.q = take((size_t)N * C * 4);
   L.coef = take((size_t)N * 2 * C * 4);
   L.v = take((size_t)N * C * 4);
-  L.part_bn = take((size_t)N * 2 * C * 4);
+  L.part_bn = take((size_t)N * 2 * C * 8);
   L.dbg = take(2 * (size_t)C * 4);
   L.da = take((size_t)N * C * HW * 4);
   L.dy = take((size_t)N * C * HW * 4);
@@ -656,7 +668,7 @@ extern "C" int halo_reduce_hfr_train_fwd(const float* feat, const float* Wr, con
   unsigned char* w8 = (unsigned char*)ws;
   float* part_sq = (float*)(w8 + L.part_sq);
   float* part_h = (float*)(w8 + L.part_h);
-  float* part_st = (float*)(w8 + L.part_st);
+  double* part_st = (double*)(w8 + L.part_st);
   float* scale = (float*)(w8 + L.scale);
   float* bn = (float*)(w8 + L.bn);
 
@@ -715,7 +727,7 @@ extern "C" int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, con
   float* q = (float*)(w8 + L.q);
   float* coef = (float*)(w8 + L.coef);
   float* v = (float*)(w8 + L.v);
-  float* part_bn = (float*)(w8 + L.part_bn);
+  double* part_bn = (double*)(w8 + L.part_bn);
   float* dbg = (float*)(w8 + L.dbg);
   float* da = (float*)(w8 + L.da);
   float* dyb = (float*)(w8 + L.dy);
@@ -742,7 +754,7 @@ extern "C" int halo_reduce_hfr_train_bwd(const float* feat, const float* Wr, con
     plane_bn_sums_kernel<<<N * C, 256, 0, st>>>(a, bn, batch_stats, v, bn_eps, part_bn, C, HW);
     rc = launch_status("plane_bn_sums_kernel");
     if (rc) return rc;
-    sum_partials_kernel<<<1, 128, 0, st>>>(part_bn, N, 2 * C, dbg);
+    sum_partials_f64_kernel<<<1, 128, 0, st>>>(part_bn, N, 2 * C, dbg);
     rc = launch_status("sum_partials_kernel");
     if (rc) return rc;
     HALO_CUDA(cudaMemcpyAsync(dbeta, dbg, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
