@@ -89,7 +89,7 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem,
       : "memory");
 }
 // round-to-nearest (ties away) to TF32 with two integer ops; ptxas expands cvt.rna.tf32.f32 into ~6 instructions
-// on sm_100a (profiles/r1_k1_tc.md).  Sign-magnitude bits: adding half an ulp of the 10-bit mantissa to the
+// on sm_100a (profiles/r1_k1.md).  Sign-magnitude bits: adding half an ulp of the 10-bit mantissa to the
 // magnitude and clearing the 13 low bits rounds correctly for both signs (inf/NaN inputs stay non-finite).
 __device__ __forceinline__ uint32_t cvt_rna_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
 // 16 feature values of one pixel (channel stride `stride` floats) -> TF32 hi (round-to-nearest) and the exact
