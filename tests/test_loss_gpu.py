@@ -22,7 +22,9 @@ def _case(N, O, h, w, H, W, seed, labelled=0.3, scale=3.0):
 
 
 @pytest.mark.parametrize("shape", [(2, 19, 20, 40, 80, 160), (1, 19, 17, 23, 50, 71), (2, 16, 12, 12, 12, 12),
-                                   (1, 5, 9, 7, 33, 20), (3, 19, 8, 16, 8, 61), (1, 19, 30, 30, 20, 25), (1, 32, 6, 6, 24, 24)])
+                                   (1, 5, 9, 7, 33, 20), (3, 19, 8, 16, 8, 61), (1, 19, 30, 30, 20, 25), (1, 32, 6, 6, 24, 24),
+                                   (1, 19, 4, 5, 64, 70),      # 16x up-sampling: footprint too large for the tiled pass B -> untiled gather
+                                   (2, 19, 40, 80, 160, 320)])  # several 8x8 tiles per image in both directions
 @pytest.mark.parametrize("neg_weight", [1.0, 0.0])
 def test_fused_loss_matches_reference_sequence(shape, neg_weight):
     N, O, h, w, H, W = shape
@@ -34,7 +36,16 @@ def test_fused_loss_matches_reference_sequence(shape, neg_weight):
     assert abs(float(loss) - float(ref_loss)) <= 1e-5 * max(1.0, abs(float(ref_loss)))
     assert abs(float(sup) - float(ref_sup)) <= 1e-5 * max(1.0, abs(float(ref_sup)))
     assert abs(float(neg) - float(ref_neg)) <= 1e-5 * max(1.0, abs(float(ref_neg)))
-    assert rel_err(x.grad, ref_g) <= 1e-5
+    # The negative-learning mask [p < threshold] is a step: a label-resolution pixel whose probability sits within fp32
+    # rounding of the threshold may take the other side than the float64 reference (once per ~1e6 pixel-classes).  Its
+    # whole contribution then differs, so the low-resolution pixels that read it are left out of the comparison.
+    up = torch.nn.functional.interpolate(logits.double(), size=(H, W), mode="bilinear", align_corners=True)
+    near = ((torch.softmax(up, dim=1) - 0.05).abs() < 2e-6).any(dim=1, keepdim=True).float()
+    low = torch.nn.functional.adaptive_max_pool2d(near, (h, w))
+    low = torch.nn.functional.max_pool2d(low, kernel_size=3, stride=1, padding=1)      # the stencil reaches one pixel further
+    keep = (low == 0).expand_as(ref_g) if neg_weight > 0 else torch.ones_like(ref_g, dtype=torch.bool)
+    assert keep.float().mean() > 0.9
+    assert rel_err(x.grad.cpu() * keep, ref_g * keep) <= 1e-5
 
 
 def test_fused_loss_edge_cases_and_determinism():
