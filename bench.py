@@ -396,12 +396,18 @@ def run_ours(args):
     counts = torch.zeros((n_images,), dtype=torch.int32, device=dev)
     launches = [0]
 
-    def step(s, k):
+    k1_events = []     # (start, end) around the K1 launch of every full-size batch of the TIMED steps (rank 0)
+
+    def step(s, k, timed=False):
         """Step k of the job = batch (k mod R) of this rank's shard; after a round's last batch, its exchange."""
         j = k % R
         b = sizes[j]
+        ev = None
+        if timed and rank == 0 and b == B:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            k1_events.append(ev)
         res = halo_b200.acquire_batch(feat[:b], P, A, cfg, gt[:b], s["active"][:b], s["selected"][:b], s["active_mask"][:b],
-                                      want_picks=True)
+                                      want_picks=True, head_events=ev)
         ex.pack(j * B, res["picks"], res["n_picked"], gt[:b])
         launches[0] += KERNELS_PER_STEP + 1
         if j == R - 1:
@@ -429,7 +435,7 @@ def run_ours(args):
     while done < args.steps:
         chunk = min(n_state, args.steps - done)
         for j in range(chunk):
-            res, b = step(state[j], args.warmup + done + j)
+            res, b = step(state[j], args.warmup + done + j, timed=True)
             images += b
         done += chunk
         if done < args.steps:  # recycle the state planes (outside the hot path; counted in the timed region)
@@ -467,14 +473,20 @@ def run_ours(args):
             halo_b200.head_forward(feat, P, A, cfg.curvature, want_logits=False, want_radius=True, want_pixunc=True)
         k1.record()
         torch.cuda.synchronize()
-        k_ms = k0.elapsed_time(k1) / reps
+        k_ms_alone = k0.elapsed_time(k1) / reps
+        # the figure the roofline is quoted on: K1 as it ran INSIDE the timed steps (events on its launch stream around every
+        # full-size batch); the back-to-back repetition above is kept beside it (it draws more power, so it clocks lower)
+        k_ms = (sum(a_.elapsed_time(b_) for a_, b_ in k1_events) / len(k1_events)) if k1_events else k_ms_alone
         alg_bytes = 4.0 * C * B * H * W  # features read once; SURVEY 8(d): radius/entropy planes are not algorithmic
         achieved = alg_bytes / (k_ms / 1e3) / 1e9
         traffic, traffic_src = traffic_from_profiles(B)
         roof = {"bound": "hbm", "kernel": "head_fwd_tc_kernel (K1 fused head, tcgen05)", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "traffic_source": traffic_src, "peak_source": peak_src,
-                "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_ms": round(k_ms, 4), "kernel_launches_timed": len(k1_events),
+                "timing": "CUDA events on the launch stream around K1 inside the timed steps (mean over the full-size batches)"
+                          if k1_events else "K1 repeated alone (no full-size batch in the timed steps)",
+                "kernel_ms_repeated_alone": round(k_ms_alone, 4), "algorithmic_bytes_per_launch": alg_bytes,
                 "step_frac": round((4.0 * C + 13) * px_total / world / (ms_total / 1e3) / 1e9 / peak, 4)}
     if distributed:
         dist.barrier()

@@ -44,20 +44,26 @@ class AcquisitionConfig:
         return math.ceil(h * w * (self.budget / self.n_rounds) / per_region)  # build.py:148-150
 
 
-def acquire_batch(feat, P, A, cfg, gt, active, selected, active_mask, *, want_score=False, want_picks=False):
+def acquire_batch(feat, P, A, cfg, gt, active, selected, active_mask, *, want_score=False, want_picks=False, head_events=None):
     """One acquisition step on a resident batch.
 
     feat (B,C,H,W) fp32 raw decoder features; gt/active/selected/active_mask (B,H,W) uint8, the last three are
-    updated IN PLACE exactly as select_pixels_to_label does.  Returns dict(n_picked (B,) int32 [, score, picks])."""
+    updated IN PLACE exactly as select_pixels_to_label does.  Returns dict(n_picked (B,) int32 [, score, picks]).
+    head_events = (start, end) CUDA events: recorded on the current stream around the fused-head launch (K1), for callers
+    that time the dominant kernel inside their own timed region (bench.py)."""
     B, C, H, W = feat.shape
     unc_mode, pixunc_mode, pur_mode, label_mode, norm_mode = modes_for(cfg.uncertainty, cfg.purity)
     need_pixunc = unc_mode != nat.UNC_ZERO
     need_label = pur_mode == nat.PUR_LABEL_HIST
     need_radius = pur_mode == nat.PUR_NORM
     need_gt = pixunc_mode == "one_minus_pgt" or label_mode == "gt_filled"
+    if head_events is not None:
+        head_events[0].record()
     res = head_forward(feat, P, A, cfg.curvature, kind="tangent", want_logits=False, want_radius=need_radius,
                        want_pixunc=need_pixunc, want_label=need_label, want_stats=False,
                        gt=gt if need_gt else None, pixunc_mode=pixunc_mode, label_mode=label_mode, norm_mode=norm_mode)
+    if head_events is not None:
+        head_events[1].record()
     r64 = st64 = None
     if pur_mode == nat.PUR_RADIUS_BINS:
         # "hyper": the K radius bins follow the reference's fp64 arithmetic (floating_region.py:94-110), which costs a
