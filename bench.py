@@ -432,9 +432,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     ev0.record()
     done, images = 0, 0
+    step_starts = []     # (start event, batch size) of every timed step on rank 0: per-step durations for the roofline block
     while done < args.steps:
         chunk = min(n_state, args.steps - done)
         for j in range(chunk):
+            if rank == 0:
+                es = torch.cuda.Event(enable_timing=True)
+                es.record()
+                step_starts.append((es, sizes[(args.warmup + done + j) % R]))
             res, b = step(state[j], args.warmup + done + j, timed=True)
             images += b
         done += chunk
@@ -477,6 +482,10 @@ def run_ours(args):
         # the figure the roofline is quoted on: K1 as it ran INSIDE the timed steps (events on its launch stream around every
         # full-size batch); the back-to-back repetition above is kept beside it (it draws more power, so it clocks lower)
         k_ms = (sum(a_.elapsed_time(b_) for a_, b_ in k1_events) / len(k1_events)) if k1_events else k_ms_alone
+        # whole-step time of the same full-size batches (start of the step to the start of the next one): at N > 1 the last
+        # batch of a shard is smaller, so ms_per_step (mean over ALL steps) is not the step K1's launch belongs to
+        full = [step_starts[i][0].elapsed_time(step_starts[i + 1][0]) for i in range(len(step_starts) - 1) if step_starts[i][1] == B]
+        step_ms_full = (sum(full) / len(full)) if full else None
         alg_bytes = 4.0 * C * B * H * W  # features read once; SURVEY 8(d): radius/entropy planes are not algorithmic
         achieved = alg_bytes / (k_ms / 1e3) / 1e9
         traffic, traffic_src = traffic_from_profiles(B)
@@ -487,6 +496,7 @@ def run_ours(args):
                 "timing": "CUDA events on the launch stream around K1 inside the timed steps (mean over the full-size batches)"
                           if k1_events else "K1 repeated alone (no full-size batch in the timed steps)",
                 "kernel_ms_repeated_alone": round(k_ms_alone, 4), "algorithmic_bytes_per_launch": alg_bytes,
+                "step_ms_full_batch": round(step_ms_full, 4) if step_ms_full else None,
                 "step_frac": round((4.0 * C + 13) * px_total / world / (ms_total / 1e3) / 1e9 / peak, 4)}
     if distributed:
         dist.barrier()
