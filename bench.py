@@ -691,7 +691,7 @@ def run_loss_step(dev, O):
         torch.cuda.synchronize()
         res[name + "_ms"] = round(e0.elapsed_time(e1) / 5, 3)
     a, b = vals["halo_seg_loss"], vals["torch_eager_sequence"]
-    res["loss_rel_diff"] = abs(float(a[0]) - float(b[0])) / abs(float(b[0]))
+    res["loss_rel_diff"] = abs(float(a[0].detach()) - float(b[0].detach())) / abs(float(b[0].detach()))
     res["grad_rel_diff_of_max"] = float((a[1] - b[1]).abs().max() / b[1].abs().max())
     res["workload"] = "fwd+bwd of CE(ignore 255) + negative-learning loss on logits %dx%dx%dx%d up-sampled to %dx%d" % (N, O, h, w, H, W)
     return res
